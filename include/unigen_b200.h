@@ -1,0 +1,127 @@
+/*
+ * unigen_b200.h -- C ABI of libunigen_b200.so: the B200 (sm_100a) implementation of the
+ * text-to-image parallel-decoding hot path of apple/ml-unigen.
+ *
+ * Every entry point takes plain device pointers and sizes; the caller (PyTorch, or anything
+ * else that owns CUDA memory) allocates all buffers including the workspace.  The library
+ * never allocates, frees, retains a pointer past the call, synchronises with the host,
+ * throws, or exits.  All work is enqueued on `stream` (a cudaStream_t passed as void*), so a
+ * T-step generation loop can be captured in a CUDA graph.
+ *
+ * Return value: 0 on success; negative UG_ERR_* for rejected arguments; positive = the
+ * cudaError_t reported by the launch.  ug_last_error() returns a thread-local message.
+ *
+ * Reference interfaces replaced (paths relative to the apple/ml-unigen tree):
+ *   ug_decode_step_bf16      models/unigen.py:407-453 (the body of the t2i_generate loop after
+ *                            the forward pass) + models/sampling.py:20-26,41-46
+ *   ug_mask_by_random_topk   models/sampling.py:41-46  mask_by_random_topk(mask_len, probs, temperature, generator)
+ *   ug_omni_attention_bf16   the attention call of the Qwen2 backbone as driven by
+ *                            models/unigen.py:260-266 with the 4-D mask built by
+ *                            training/prompting_utils.py:975-1020 (create_attention_mask_predict_next,
+ *                            rm_pad_in_image=True); plug-in point = transformers attention-function
+ *                            interface fn(module, q[B,Hq,L,D], k[B,Hkv,L,D], v, attention_mask, scaling=...)
+ *   ug_export_noise          (test hook) the exponential / uniform tensors that
+ *                            torch.multinomial (unigen.py:419) and gumbel_noise (sampling.py:24-26)
+ *                            would have drawn, as generated inside the kernel
+ */
+#ifndef UNIGEN_B200_H_
+#define UNIGEN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UG_ABI_VERSION 1
+
+enum {
+    UG_OK = 0,
+    UG_ERR_NULL = -1,        /* a required pointer is NULL */
+    UG_ERR_SHAPE = -2,       /* unsupported B/N/V/L/heads/head_dim */
+    UG_ERR_ALIGN = -3,       /* pointer or stride not aligned as documented */
+    UG_ERR_WORKSPACE = -4,   /* workspace too small */
+    UG_ERR_ARG = -5,         /* other invalid argument */
+    UG_ERR_DEVICE = -6       /* not an sm_100 device / driver entry point missing */
+};
+
+int ug_abi_version(void);
+const char* ug_last_error(void);
+
+/* ---- decode step -----------------------------------------------------------------------------
+ * One MaskGIT step for B images of N tokens over a V-entry codebook.
+ *   logits          bf16 [B,N,V], dense, 16-byte aligned          (image rows x codebook columns)
+ *   uncond_logits   NULL, or bf16 [B,N,V]: logits = bf16(bf16(scale*bf16(cond-uncond))+uncond)
+ *   ids_inout       int64 [B,N]: current ids (mask_token_id = still unknown); rewritten in place
+ *                   to  masking ? mask_token_id : sampled
+ *   sampled_out     int64 [B,N]: sampled ids with already-known ids kept (the value t2i_generate returns)
+ *   mask_out        uint8 [B,N]: 1 where the token is re-masked for the next step
+ *   sel_prob_out    NULL or float [B,N]: selected_probs (FLT_MAX for known tokens)
+ *   conf_out        NULL or float [B,N]: confidence used by the mask selection
+ *   q_noise         NULL -> in-kernel Philox; else float [B,N,V] Exp(1) noise (the tensor
+ *                   torch.multinomial would draw)
+ *   u_noise         NULL -> in-kernel Philox; else float [B,N] U[0,1) noise (gumbel_noise's)
+ *   philox_seed/offset  key and per-step offset of the in-kernel streams; batch_offset is the
+ *                   global index of image 0 of this call, so sharding a batch across GPUs
+ *                   does not change any image
+ *   mask_len_cap    floor(N * mask_ratio) computed by the host in float32 (may be -1)
+ *   temperature     annealed temperature of this step (already compounded by the host)
+ *   workspace       ug_decode_step_workspace_bytes(B,N,V) bytes, zero-filled ONCE before the
+ *                   first call (the kernel leaves it zeroed); one workspace per stream
+ * Supported: V in {4096, 8192, 16384}; 2 <= N <= 4096; 1 <= B; B*N < 2^31.
+ */
+size_t ug_decode_step_workspace_bytes(int B, int N, int V);
+
+int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float guidance_scale,
+                        int64_t* ids_inout, int64_t* sampled_out, uint8_t* mask_out,
+                        float* sel_prob_out, float* conf_out,
+                        const float* q_noise, const float* u_noise,
+                        uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
+                        int B, int N, int V, int64_t mask_token_id, int mask_len_cap, float temperature,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- mask_by_random_topk ---------------------------------------------------------------------
+ *   probs float [B,N]; mask_len int64 [B] (already clamped by the caller, 0 <= mask_len < N);
+ *   u_noise NULL -> Philox (seed, offset, batch_offset) else float [B,N]; mask_out uint8 [B,N].
+ *   masking = confidence < sort(confidence)[mask_len],
+ *   confidence = log(clamp(probs,1e-20)) + temperature * gumbel(u).   2 <= N <= 4096. */
+int ug_mask_by_random_topk(const float* probs, const int64_t* mask_len, const float* u_noise,
+                           uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
+                           float temperature, uint8_t* mask_out, float* conf_out,
+                           int B, int N, void* stream);
+
+/* ---- noise export (test hook) ---------------------------------------------------------------- */
+int ug_export_noise(uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
+                    int B, int N, int V, float* q_out /* [B,N,V] or NULL */, float* u_out /* [B,N] or NULL */,
+                    void* stream);
+
+/* test hook: softmax denominators of subsequent decode steps of this thread (float [B,N]; NULL = off) */
+void ug_debug_set_rowsum_out(float* rowsum_out);
+/* test hook: nonzero = evaluate every element of the race exactly (exercises the rare fallback path) */
+void ug_debug_set_force_full_race(int on);
+
+/* ---- omni attention --------------------------------------------------------------------------
+ * out = softmax(q k^T * scale + M) v per head, with the omni mask M given in closed form by two
+ * integers per sequence:
+ *     row i <  pad_len[b]             : columns j <= i                (pad rows; outputs unused)
+ *     pad_len[b] <= i < soi_idx[b]    : columns pad_len[b] <= j <= i  (text: causal, never sees pads)
+ *     i >= soi_idx[b]                 : columns j >= pad_len[b]       (<soi>, image block, <eoi>: bidirectional)
+ *   q   bf16 [B,L,Hq,D]   (element strides q_stride_b, q_stride_l, q_stride_h; D contiguous)
+ *   k,v bf16 [B,L,Hkv,D]  (kv_stride_b, kv_stride_l, kv_stride_h)
+ *   out bf16 [B,L,Hq,D]   (o_stride_b, o_stride_l, o_stride_h)
+ *   pad_len, soi_idx int32 [B] on the device
+ * Supported: D = 128, Hq % Hkv == 0, all strides multiples of 8 elements, 16-byte aligned bases.
+ */
+int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* out,
+                           const int32_t* pad_len, const int32_t* soi_idx,
+                           int B, int L, int Hq, int Hkv, int D, float scale,
+                           int64_t q_stride_b, int64_t q_stride_l, int64_t q_stride_h,
+                           int64_t kv_stride_b, int64_t kv_stride_l, int64_t kv_stride_h,
+                           int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIGEN_B200_H_ */

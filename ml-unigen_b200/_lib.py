@@ -1,0 +1,77 @@
+"""ctypes binding of libunigen_b200.so (C ABI: include/unigen_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  A missing library
+or a missing symbol is a hard error -- the product has no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libunigen_b200.so")
+
+UG_ABI_VERSION = 1
+SYMBOLS = (
+    "ug_abi_version", "ug_last_error", "ug_decode_step_workspace_bytes", "ug_decode_step_bf16",
+    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_debug_set_rowsum_out", "ug_debug_set_force_full_race",
+)
+
+_lib = None
+
+
+class UnigenB200Error(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UnigenB200Error(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a).  There is no fallback path.")
+    L = ctypes.CDLL(LIB_PATH)
+    for s in SYMBOLS:
+        if not hasattr(L, s):
+            raise UnigenB200Error(f"{LIB_PATH} does not export {s}")
+    c = ctypes
+    L.ug_abi_version.restype = c.c_int
+    L.ug_last_error.restype = c.c_char_p
+    L.ug_decode_step_workspace_bytes.restype = c.c_size_t
+    L.ug_decode_step_workspace_bytes.argtypes = [c.c_int, c.c_int, c.c_int]
+    L.ug_decode_step_bf16.restype = c.c_int
+    L.ug_decode_step_bf16.argtypes = [
+        c.c_void_p, c.c_void_p, c.c_float,
+        c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
+        c.c_void_p, c.c_void_p,
+        c.c_uint64, c.c_uint64, c.c_int64,
+        c.c_int, c.c_int, c.c_int, c.c_int64, c.c_int, c.c_float,
+        c.c_void_p, c.c_size_t, c.c_void_p]
+    L.ug_mask_by_random_topk.restype = c.c_int
+    L.ug_mask_by_random_topk.argtypes = [
+        c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64, c.c_uint64, c.c_int64,
+        c.c_float, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_void_p]
+    L.ug_export_noise.restype = c.c_int
+    L.ug_export_noise.argtypes = [c.c_uint64, c.c_uint64, c.c_int64, c.c_int, c.c_int, c.c_int,
+                                  c.c_void_p, c.c_void_p, c.c_void_p]
+    L.ug_omni_attention_bf16.restype = c.c_int
+    L.ug_omni_attention_bf16.argtypes = [
+        c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
+        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_float,
+        c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_int64,
+        c.c_void_p]
+    L.ug_debug_set_rowsum_out.restype = None
+    L.ug_debug_set_rowsum_out.argtypes = [c.c_void_p]
+    L.ug_debug_set_force_full_race.restype = None
+    L.ug_debug_set_force_full_race.argtypes = [c.c_int]
+    if L.ug_abi_version() != UG_ABI_VERSION:
+        raise UnigenB200Error(f"ABI version {L.ug_abi_version()} != {UG_ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise UnigenB200Error(f"libunigen_b200 rc={rc}: {lib().ug_last_error().decode()}")

@@ -1,0 +1,39 @@
+// decode_step.h -- internal launch interface of the fused decode-step kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ugk {
+
+struct DecodeArgs {
+    const uint16_t* logits;      // bf16 [B,N,V]
+    const uint16_t* uncond;      // bf16 [B,N,V] or null
+    float guidance;
+    long long* ids;              // int64 [B,N] in/out
+    long long* sampled;          // int64 [B,N]
+    uint8_t* mask;               // [B,N]
+    float* sel_prob_out;         // nullable
+    float* conf_out;             // nullable
+    float* rowsum_out;           // nullable (debug: softmax denominators)
+    const float* q_noise;        // nullable
+    const float* u_noise;        // nullable
+    uint64_t seed, offset;
+    int64_t batch_offset;
+    int B, N, V;
+    long long mask_id;
+    int cap;
+    float temperature;
+    int force_full_race;         // test hook: skip the candidate filter, evaluate every element
+    // workspace
+    float* psel;                 // [B*N] selected probabilities (FLT_MAX = known)
+    unsigned* counters;          // [B] rows finished per image
+    unsigned* ticket;            // row-pair ticket
+    unsigned* cta_done;          // producers finished
+};
+
+cudaError_t launch_decode_step(const DecodeArgs& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_topk(const DecodeArgs& a, const int64_t* mask_len, cudaStream_t stream);
+cudaError_t launch_export_noise(uint64_t seed, uint64_t offset, int64_t batch_offset, int B, int N, int V,
+                                float* q_out, float* u_out, cudaStream_t stream);
+
+}  // namespace ugk

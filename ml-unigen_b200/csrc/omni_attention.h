@@ -1,0 +1,22 @@
+// omni_attention.h -- internal launch interface of the tcgen05 omni-attention kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace ugk {
+
+struct AttnArgs {
+    const void* q; const void* k; const void* v; void* out;
+    const int32_t* pad_len; const int32_t* soi_idx;
+    int B, L, Hq, Hkv;
+    float scale;
+    int64_t q_sb, q_sl, q_sh;
+    int64_t kv_sb, kv_sl, kv_sh;
+    int64_t o_sb, o_sl, o_sh;
+};
+
+// returns 0, a negative UG_ERR_* code, or a positive cudaError_t; msg receives a description
+int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, char* msg, size_t msg_len);
+
+}  // namespace ugk

@@ -1,0 +1,197 @@
+// ug_capi.cu -- extern "C" boundary of libunigen_b200.so (see include/unigen_b200.h).
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "unigen_b200.h"
+#include "decode_step.h"
+#include "omni_attention.h"
+
+float* ugk_debug_rowsum_out();
+int ugk_debug_force_full_race();
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// per-device SM count, cached (cudaGetDevice/cudaDeviceGetAttribute do not synchronise)
+int sm_count(int* cc_major)
+{
+    static thread_local int cached_dev = -1, cached_sms = 0, cached_major = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&cached_major, cudaDevAttrComputeCapabilityMajor, dev);
+        cached_dev = dev;
+    }
+    if (cc_major) *cc_major = cached_major;
+    return cached_sms;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+int ug_abi_version(void) { return UG_ABI_VERSION; }
+
+const char* ug_last_error(void) { return g_err; }
+
+size_t ug_decode_step_workspace_bytes(int B, int N, int V)
+{
+    (void)V;
+    if (B <= 0 || N <= 0) return 0;
+    // [counters B][ticket][cta_done] padded to 256 B, then psel float[B*N]
+    return align_up(sizeof(unsigned) * ((size_t)B + 2), 256) + sizeof(float) * (size_t)B * N;
+}
+
+int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float guidance_scale,
+                        int64_t* ids_inout, int64_t* sampled_out, uint8_t* mask_out,
+                        float* sel_prob_out, float* conf_out,
+                        const float* q_noise, const float* u_noise,
+                        uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
+                        int B, int N, int V, int64_t mask_token_id, int mask_len_cap, float temperature,
+                        void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!logits || !ids_inout || !sampled_out || !mask_out || !workspace)
+        return fail(UG_ERR_NULL, "ug_decode_step_bf16: logits, ids_inout, sampled_out, mask_out and workspace are required");
+    if (V != 4096 && V != 8192 && V != 16384)
+        return fail(UG_ERR_SHAPE, "ug_decode_step_bf16: V=%d unsupported (4096, 8192, 16384)", V);
+    if (B < 1 || N < 2 || N > 4096 || (long long)B * N >= (1ll << 31))
+        return fail(UG_ERR_SHAPE, "ug_decode_step_bf16: B=%d N=%d unsupported (B>=1, 2<=N<=4096, B*N<2^31)", B, N);
+    if (!aligned16(logits) || !aligned16(uncond_logits) || !aligned16(q_noise) || !aligned16(workspace))
+        return fail(UG_ERR_ALIGN, "ug_decode_step_bf16: logits, uncond_logits, q_noise and workspace must be 16-byte aligned");
+    if (workspace_bytes < ug_decode_step_workspace_bytes(B, N, V))
+        return fail(UG_ERR_WORKSPACE, "ug_decode_step_bf16: workspace %zu < %zu bytes", workspace_bytes,
+                    ug_decode_step_workspace_bytes(B, N, V));
+    int major = 0;
+    const int sms = sm_count(&major);
+    if (sms <= 0 || major < 10) return fail(UG_ERR_DEVICE, "ug_decode_step_bf16: needs an sm_100 device (cc major %d)", major);
+
+    ugk::DecodeArgs a;
+    memset(&a, 0, sizeof a);
+    a.logits = static_cast<const uint16_t*>(logits);
+    a.uncond = static_cast<const uint16_t*>(uncond_logits);
+    a.guidance = guidance_scale;
+    a.ids = reinterpret_cast<long long*>(ids_inout);
+    a.sampled = reinterpret_cast<long long*>(sampled_out);
+    a.mask = mask_out;
+    a.sel_prob_out = sel_prob_out;
+    a.conf_out = conf_out;
+    a.rowsum_out = ugk_debug_rowsum_out();
+    a.force_full_race = ugk_debug_force_full_race();
+    a.q_noise = q_noise;
+    a.u_noise = u_noise;
+    a.seed = philox_seed;
+    a.offset = philox_offset;
+    a.batch_offset = batch_offset;
+    a.B = B; a.N = N; a.V = V;
+    a.mask_id = mask_token_id;
+    a.cap = mask_len_cap;
+    a.temperature = temperature;
+    unsigned* w = static_cast<unsigned*>(workspace);
+    a.counters = w;
+    a.ticket = w + B;
+    a.cta_done = w + B + 1;
+    a.psel = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up(sizeof(unsigned) * ((size_t)B + 2), 256));
+    cudaError_t e = ugk::launch_decode_step(a, sms, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_decode_step_bf16 launch");
+    return UG_OK;
+}
+
+int ug_mask_by_random_topk(const float* probs, const int64_t* mask_len, const float* u_noise,
+                           uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
+                           float temperature, uint8_t* mask_out, float* conf_out,
+                           int B, int N, void* stream)
+{
+    if (!probs || !mask_len || !mask_out) return fail(UG_ERR_NULL, "ug_mask_by_random_topk: probs, mask_len, mask_out are required");
+    if (B < 1 || N < 2 || N > 4096) return fail(UG_ERR_SHAPE, "ug_mask_by_random_topk: B=%d N=%d unsupported (2<=N<=4096)", B, N);
+    ugk::DecodeArgs a;
+    memset(&a, 0, sizeof a);
+    a.psel = const_cast<float*>(probs);
+    a.u_noise = u_noise;
+    a.seed = philox_seed;
+    a.offset = philox_offset;
+    a.batch_offset = batch_offset;
+    a.B = B; a.N = N;
+    a.temperature = temperature;
+    a.mask = mask_out;
+    a.conf_out = conf_out;
+    cudaError_t e = ugk::launch_topk(a, mask_len, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_mask_by_random_topk launch");
+    return UG_OK;
+}
+
+int ug_export_noise(uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
+                    int B, int N, int V, float* q_out, float* u_out, void* stream)
+{
+    if (!q_out && !u_out) return fail(UG_ERR_NULL, "ug_export_noise: nothing to write");
+    if (B < 1 || N < 1 || V < 1) return fail(UG_ERR_SHAPE, "ug_export_noise: bad shape");
+    cudaError_t e = ugk::launch_export_noise(philox_seed, philox_offset, batch_offset, B, N, V, q_out, u_out,
+                                             static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_export_noise launch");
+    return UG_OK;
+}
+
+int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* out,
+                           const int32_t* pad_len, const int32_t* soi_idx,
+                           int B, int L, int Hq, int Hkv, int D, float scale,
+                           int64_t q_stride_b, int64_t q_stride_l, int64_t q_stride_h,
+                           int64_t kv_stride_b, int64_t kv_stride_l, int64_t kv_stride_h,
+                           int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
+                           void* stream)
+{
+    if (!q || !k || !v || !out || !pad_len || !soi_idx) return fail(UG_ERR_NULL, "ug_omni_attention_bf16: null pointer");
+    if (D != 128 || Hkv < 1 || Hq % Hkv != 0 || B < 1 || L < 1)
+        return fail(UG_ERR_SHAPE, "ug_omni_attention_bf16: B=%d L=%d Hq=%d Hkv=%d D=%d unsupported (D=128, Hq%%Hkv==0)", B, L, Hq, Hkv, D);
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out) ||
+        ((q_stride_b | q_stride_l | q_stride_h | kv_stride_b | kv_stride_l | kv_stride_h | o_stride_b | o_stride_l | o_stride_h) & 7))
+        return fail(UG_ERR_ALIGN, "ug_omni_attention_bf16: bases must be 16-byte aligned and strides multiples of 8 elements");
+    int major = 0;
+    const int sms = sm_count(&major);
+    if (sms <= 0 || major < 10) return fail(UG_ERR_DEVICE, "ug_omni_attention_bf16: needs an sm_100 device (cc major %d)", major);
+    ugk::AttnArgs a;
+    a.q = q; a.k = k; a.v = v; a.out = out;
+    a.pad_len = pad_len; a.soi_idx = soi_idx;
+    a.B = B; a.L = L; a.Hq = Hq; a.Hkv = Hkv; a.scale = scale;
+    a.q_sb = q_stride_b; a.q_sl = q_stride_l; a.q_sh = q_stride_h;
+    a.kv_sb = kv_stride_b; a.kv_sl = kv_stride_l; a.kv_sh = kv_stride_h;
+    a.o_sb = o_stride_b; a.o_sl = o_stride_l; a.o_sh = o_stride_h;
+    char msg[256] = "";
+    int rc = ugk::launch_omni_attention(a, sms, static_cast<cudaStream_t>(stream), msg, sizeof msg);
+    if (rc != 0) { snprintf(g_err, sizeof g_err, "ug_omni_attention_bf16: %s", msg); return rc; }
+    return UG_OK;
+}
+
+}  // extern "C"
+
+// test hook: when set, the next decode steps issued from this thread also write the softmax
+// denominators (float [B,N], 0 for known rows) so tests can compare them bit for bit.
+static thread_local float* g_rowsum_out = nullptr;
+extern "C" void ug_debug_set_rowsum_out(float* p) { g_rowsum_out = p; }
+float* ugk_debug_rowsum_out() { return g_rowsum_out; }
+
+// test hook: force the exact whole-row evaluation of the race (the e^-16 fallback) on every row
+static thread_local int g_force_full_race = 0;
+extern "C" void ug_debug_set_force_full_race(int on) { g_force_full_race = on; }
+int ugk_debug_force_full_race() { return g_force_full_race; }

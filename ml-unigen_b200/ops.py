@@ -1,0 +1,133 @@
+"""Tensor-level wrappers over the C ABI (include/unigen_b200.h).
+
+PyTorch is used here only for device memory and streams: every function takes CUDA tensors,
+passes `data_ptr()`s and the current stream to libunigen_b200.so and returns without
+synchronising.  Nothing here computes on the host or falls back to torch operators.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_FLT_MAX = torch.finfo(torch.float32).max
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.UnigenB200Error("unigen-b200 kernels need CUDA tensors (there is no CPU path)")
+
+
+class DecodeWorkspace:
+    """Caller-owned workspace of the decode step (zeroed once; the kernel re-arms it)."""
+
+    def __init__(self, B: int, N: int, V: int, device):
+        self.B, self.N, self.V = B, N, V
+        self.nbytes = _lib.lib().ug_decode_step_workspace_bytes(B, N, V)
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+
+
+def decode_step(logits: torch.Tensor, ids_inout: torch.Tensor, *, mask_token_id: int, mask_len_cap: int,
+                temperature: float, workspace: DecodeWorkspace,
+                sampled_out: Optional[torch.Tensor] = None, mask_out: Optional[torch.Tensor] = None,
+                sel_prob_out: Optional[torch.Tensor] = None, conf_out: Optional[torch.Tensor] = None,
+                uncond_logits: Optional[torch.Tensor] = None, guidance_scale: float = 0.0,
+                q_noise: Optional[torch.Tensor] = None, u_noise: Optional[torch.Tensor] = None,
+                seed: int = 0, offset: int = 0, batch_offset: int = 0):
+    """One fused MaskGIT step (models/unigen.py:407-453).  `ids_inout` int64 [B,N] is updated in
+    place; returns (sampled_ids int64 [B,N], masking uint8 [B,N])."""
+    _need_cuda(logits, ids_inout)
+    if logits.dtype != torch.bfloat16 or logits.dim() != 3 or not logits.is_contiguous():
+        raise ValueError("logits must be a contiguous bf16 [B,N,V] tensor")
+    B, N, V = logits.shape
+    if ids_inout.dtype != torch.int64 or tuple(ids_inout.shape) != (B, N) or not ids_inout.is_contiguous():
+        raise ValueError("ids_inout must be a contiguous int64 [B,N] tensor")
+    if (workspace.B, workspace.N, workspace.V) != (B, N, V):
+        raise ValueError("workspace was sized for a different shape")
+    dev = logits.device
+    if sampled_out is None:
+        sampled_out = torch.empty(B, N, dtype=torch.int64, device=dev)
+    if mask_out is None:
+        mask_out = torch.empty(B, N, dtype=torch.uint8, device=dev)
+    for t, dt, shp in ((uncond_logits, torch.bfloat16, (B, N, V)), (q_noise, torch.float32, (B, N, V)),
+                       (u_noise, torch.float32, (B, N)), (sel_prob_out, torch.float32, (B, N)),
+                       (conf_out, torch.float32, (B, N)), (sampled_out, torch.int64, (B, N)),
+                       (mask_out, torch.uint8, (B, N))):
+        if t is not None and (t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous() or t.device != dev):
+            raise ValueError(f"bad optional tensor: expected contiguous {dt} {shp} on {dev}")
+    rc = _lib.lib().ug_decode_step_bf16(
+        _ptr(logits), _ptr(uncond_logits), float(guidance_scale),
+        _ptr(ids_inout), _ptr(sampled_out), _ptr(mask_out), _ptr(sel_prob_out), _ptr(conf_out),
+        _ptr(q_noise), _ptr(u_noise), seed & (2**64 - 1), offset & (2**64 - 1), batch_offset,
+        B, N, V, mask_token_id, int(mask_len_cap), float(temperature),
+        _ptr(workspace.buf), workspace.nbytes, _stream())
+    _lib.check(rc)
+    return sampled_out, mask_out
+
+
+def mask_by_random_topk(probs: torch.Tensor, mask_len: torch.Tensor, temperature: float, *,
+                        u_noise: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
+                        batch_offset: int = 0, conf_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """models/sampling.py:41-46 on the device.  probs float32 [B,N]; mask_len int64 [B] or [B,1]."""
+    _need_cuda(probs, mask_len)
+    if probs.dtype != torch.float32 or probs.dim() != 2:
+        raise ValueError("probs must be float32 [B,N]")
+    probs = probs.contiguous()
+    B, N = probs.shape
+    ml = mask_len.reshape(-1).to(torch.int64).contiguous()
+    if ml.numel() != B:
+        raise ValueError("mask_len must have one entry per row")
+    out = torch.empty(B, N, dtype=torch.uint8, device=probs.device)
+    rc = _lib.lib().ug_mask_by_random_topk(_ptr(probs), _ptr(ml), _ptr(u_noise), seed & (2**64 - 1),
+                                           offset & (2**64 - 1), batch_offset, float(temperature),
+                                           _ptr(out), _ptr(conf_out), B, N, _stream())
+    _lib.check(rc)
+    return out.view(torch.bool)
+
+
+def export_noise(seed: int, offset: int, B: int, N: int, V: int, device, batch_offset: int = 0,
+                 want_q: bool = True, want_u: bool = True):
+    """(q float32 [B,N,V], u float32 [B,N]) exactly as the Philox mode of decode_step draws them."""
+    q = torch.empty(B, N, V, dtype=torch.float32, device=device) if want_q else None
+    u = torch.empty(B, N, dtype=torch.float32, device=device) if want_u else None
+    rc = _lib.lib().ug_export_noise(seed & (2**64 - 1), offset & (2**64 - 1), batch_offset, B, N, V,
+                                    _ptr(q), _ptr(u), _stream())
+    _lib.check(rc)
+    return q, u
+
+
+def omni_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_len: torch.Tensor,
+                   soi_idx: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Omni attention.  q [B,L,Hq,D], k/v [B,L,Hkv,D] bf16 (last dim contiguous, arbitrary other
+    strides); pad_len / soi_idx int32 [B].  Returns out [B,L,Hq,D] bf16."""
+    _need_cuda(q, k, v, pad_len, soi_idx)
+    B, L, Hq, D = q.shape
+    Hkv = k.shape[2]
+    if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
+        raise ValueError("q, k, v must be bf16")
+    if q.stride(3) != 1 or k.stride(3) != 1 or v.stride(3) != 1:
+        raise ValueError("head_dim must be contiguous")
+    if k.stride() != v.stride() or k.shape != v.shape:
+        raise ValueError("k and v must share shape and strides")
+    if pad_len.dtype != torch.int32 or soi_idx.dtype != torch.int32:
+        raise ValueError("pad_len / soi_idx must be int32")
+    if out is None:
+        out = torch.empty(B, L, Hq, D, dtype=torch.bfloat16, device=q.device)
+    rc = _lib.lib().ug_omni_attention_bf16(
+        _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(pad_len), _ptr(soi_idx),
+        B, L, Hq, Hkv, D, float(scale),
+        q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
+        out.stride(0), out.stride(1), out.stride(2), _stream())
+    _lib.check(rc)
+    return out

