@@ -121,6 +121,10 @@ int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* ou
                            int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
                            void* stream);
 
+/* test hook: float[2*128*128] receiving the raw scores S and the bf16 probabilities P of the first kv tile
+ * of the first query tile of (b=0, h=0) of subsequent ug_omni_attention_bf16 calls of this thread; NULL = off */
+void ug_debug_set_attn_dump(float* dump);
+
 #ifdef __cplusplus
 }
 #endif

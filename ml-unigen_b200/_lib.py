@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libunigen_b200.so")
 UG_ABI_VERSION = 1
 SYMBOLS = (
     "ug_abi_version", "ug_last_error", "ug_decode_step_workspace_bytes", "ug_decode_step_bf16",
-    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_debug_set_rowsum_out", "ug_debug_set_force_full_race",
+    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_debug_set_rowsum_out", "ug_debug_set_force_full_race", "ug_debug_set_attn_dump",
 )
 
 _lib = None
@@ -66,6 +66,8 @@ def lib() -> ctypes.CDLL:
     L.ug_debug_set_rowsum_out.argtypes = [c.c_void_p]
     L.ug_debug_set_force_full_race.restype = None
     L.ug_debug_set_force_full_race.argtypes = [c.c_int]
+    L.ug_debug_set_attn_dump.restype = None
+    L.ug_debug_set_attn_dump.argtypes = [c.c_void_p]
     if L.ug_abi_version() != UG_ABI_VERSION:
         raise UnigenB200Error(f"ABI version {L.ug_abi_version()} != {UG_ABI_VERSION}")
     _lib = L

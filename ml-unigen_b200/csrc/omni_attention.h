@@ -16,6 +16,10 @@ struct AttnArgs {
     int64_t o_sb, o_sl, o_sh;
 };
 
+// test hook: float[2*128*128] receiving S (raw q.k) and P (bf16-rounded probabilities) of kv tile 0 of the
+// FIRST q tile (rows 0..127) of (b=0, h=0); nullptr = off
+void set_attn_debug(float* p);
+
 // returns 0, a negative UG_ERR_* code, or a positive cudaError_t; msg receives a description
 int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, char* msg, size_t msg_len);
 

@@ -195,3 +195,5 @@ float* ugk_debug_rowsum_out() { return g_rowsum_out; }
 static thread_local int g_force_full_race = 0;
 extern "C" void ug_debug_set_force_full_race(int on) { g_force_full_race = on; }
 int ugk_debug_force_full_race() { return g_force_full_race; }
+
+extern "C" void ug_debug_set_attn_dump(float* p) { ugk::set_attn_debug(p); }
