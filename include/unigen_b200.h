@@ -121,6 +121,23 @@ int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* ou
                            int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
                            void* stream);
 
+/* ---- row-wise kernels of the Qwen2 decoder layer (transformers models/qwen2/modeling_qwen2.py) ------------
+ * The GEMMs around them stay on cuBLAS in this round; these four replace the
+ * ATen elementwise chains of Qwen2RMSNorm (+ residual add), apply_rotary_pos_emb, Qwen2MLP's
+ * act_fn(gate)*up and embed_tokens (models/unigen.py:370, 452).
+ *   ug_add_rmsnorm : x fp32 [M,H] (+= delta bf16 [M,H] if non-NULL, written back); out bf16 [M,H] =
+ *                    weight * x * rsqrt(mean(x^2) + eps).  H % 256 == 0, H <= 8192.
+ *   ug_rope_qk     : in-place rotate_half RoPE on the q and k heads of qkv bf16 [M,(Hq+2Hkv)*D];
+ *                    position = m % L; cos/sin fp32 [L, D/2].
+ *   ug_swiglu      : act bf16 [M,I] = silu(g) * u, gate_up bf16 [M,2I] = [g | u].
+ *   ug_embed_rows  : x fp32 [M,H] = table bf16 [vocab,H][tokens[m]].
+ */
+int ug_add_rmsnorm(float* x, const void* delta_bf16, const void* weight_bf16, void* out_bf16,
+                   int64_t M, int H, float eps, void* stream);
+int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, int64_t M, int L, int Hq, int Hkv, int D, void* stream);
+int ug_swiglu(const void* gate_up_bf16, void* act_bf16, int64_t M, int I, void* stream);
+int ug_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64_t M, int H, int64_t vocab, void* stream);
+
 /* test hook: float[2*128*128] receiving the raw scores S and the bf16 probabilities P of the first kv tile
  * of the first query tile of (b=0, h=0) of subsequent ug_omni_attention_bf16 calls of this thread; NULL = off */
 void ug_debug_set_attn_dump(float* dump);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libunigen_b200.so")
 UG_ABI_VERSION = 1
 SYMBOLS = (
     "ug_abi_version", "ug_last_error", "ug_decode_step_workspace_bytes", "ug_decode_step_bf16",
-    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_debug_set_rowsum_out", "ug_debug_set_force_full_race", "ug_debug_set_attn_dump",
+    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_debug_set_rowsum_out", "ug_debug_set_force_full_race", "ug_debug_set_attn_dump", "ug_add_rmsnorm", "ug_rope_qk", "ug_swiglu", "ug_embed_rows",
 )
 
 _lib = None
@@ -68,6 +68,14 @@ def lib() -> ctypes.CDLL:
     L.ug_debug_set_force_full_race.argtypes = [c.c_int]
     L.ug_debug_set_attn_dump.restype = None
     L.ug_debug_set_attn_dump.argtypes = [c.c_void_p]
+    L.ug_add_rmsnorm.restype = c.c_int
+    L.ug_add_rmsnorm.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_float, c.c_void_p]
+    L.ug_rope_qk.restype = c.c_int
+    L.ug_rope_qk.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p]
+    L.ug_swiglu.restype = c.c_int
+    L.ug_swiglu.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_void_p]
+    L.ug_embed_rows.restype = c.c_int
+    L.ug_embed_rows.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_int64, c.c_void_p]
     if L.ug_abi_version() != UG_ABI_VERSION:
         raise UnigenB200Error(f"ABI version {L.ug_abi_version()} != {UG_ABI_VERSION}")
     _lib = L

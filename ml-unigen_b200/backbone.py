@@ -1,0 +1,168 @@
+"""Qwen2.5 decoder stack as the T2I path runs it (transformers Qwen2Model.forward with
+`inputs_embeds` + the 4-D omni mask, reached from apple/ml-unigen models/unigen.py:260-266),
+laid out for one B200:
+
+* weights resident in HBM as bf16: fused [q|k|v] projection (+bias), o_proj, fused [gate|up], down,
+  RMSNorm gains, tied embedding / LM head (3.1 GB at 1.5 B parameters -- replicated per GPU);
+* fp32 residual stream (what the reference's bf16-autocast mode keeps), bf16 activations between
+  GEMMs, every elementwise chain fused into one hand-written row kernel (ops.add_rmsnorm, rope_qk_,
+  swiglu, embed_rows);
+* attention through the tcgen05 omni-attention kernel on strided views of the fused qkv activation --
+  no repeat_kv, no dense mask;
+* the LM head is applied only to the N image rows and only to the V codebook rows of the tied
+  embedding (models/unigen.py:416 slices exactly that block out of the full-vocabulary logits),
+  producing the dense bf16 [B,N,V] tensor the decode-step kernel streams;
+* the dense GEMMs are cuBLAS (torch.nn.functional.linear) in this round.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+@dataclass
+class QwenConfig:
+    hidden_size: int = 1536
+    intermediate_size: int = 8960
+    num_hidden_layers: int = 28
+    num_attention_heads: int = 12
+    num_key_value_heads: int = 2
+    head_dim: int = 128
+    vocab_size: int = 159867          # len(tokenizer) + 8192 + 1 (evaluation/inference_geneval.py:104)
+    rope_theta: float = 1000000.0
+    rms_norm_eps: float = 1e-6
+
+    def as_dict(self):
+        return dict(self.__dict__)
+
+
+class QwenBackboneB200:
+    """Inference-only decoder stack.  `weights` uses transformers' Qwen2Model parameter names
+    (`embed_tokens.weight`, `layers.{i}.self_attn.q_proj.weight`, ..., `norm.weight`)."""
+
+    def __init__(self, cfg: QwenConfig, weights: Dict[str, torch.Tensor], device):
+        if not torch.cuda.is_available():
+            raise RuntimeError("QwenBackboneB200 needs a CUDA device (no CPU path)")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        bf = lambda t: t.detach().to(self.device, torch.bfloat16).contiguous()
+        self.embed = bf(weights["embed_tokens.weight"])
+        self.final_norm = bf(weights["norm.weight"])
+        self.layers = []
+        for l in range(cfg.num_hidden_layers):
+            p = f"layers.{l}."
+            self.layers.append(dict(
+                ln1=bf(weights[p + "input_layernorm.weight"]),
+                wqkv=bf(torch.cat([weights[p + "self_attn.q_proj.weight"], weights[p + "self_attn.k_proj.weight"],
+                                   weights[p + "self_attn.v_proj.weight"]], 0)),
+                bqkv=bf(torch.cat([weights[p + "self_attn.q_proj.bias"], weights[p + "self_attn.k_proj.bias"],
+                                   weights[p + "self_attn.v_proj.bias"]], 0)),
+                wo=bf(weights[p + "self_attn.o_proj.weight"]),
+                ln2=bf(weights[p + "post_attention_layernorm.weight"]),
+                wgu=bf(torch.cat([weights[p + "mlp.gate_proj.weight"], weights[p + "mlp.up_proj.weight"]], 0)),
+                wd=bf(weights[p + "mlp.down_proj.weight"]),
+            ))
+        self._rope_cache = {}
+        self.attn_events = None        # bench hook: list receiving (start, end) CUDA events of every attention launch
+
+    # -------------------------------------------------------------------------------------------
+    @classmethod
+    def random_init(cls, cfg: QwenConfig, device, seed: int = 0, std: float = 0.02) -> "QwenBackboneB200":
+        """Random-init weights of the named architecture, generated directly on the GPU (bf16)."""
+        g = torch.Generator(device=device).manual_seed(seed)
+        H, I, D = cfg.hidden_size, cfg.intermediate_size, cfg.head_dim
+        Hq, Hkv = cfg.num_attention_heads, cfg.num_key_value_heads
+        rn = lambda *s: (torch.randn(*s, device=device, generator=g, dtype=torch.float32) * std).bfloat16()
+        w = {"embed_tokens.weight": rn(cfg.vocab_size, H), "norm.weight": torch.ones(H, device=device)}
+        for l in range(cfg.num_hidden_layers):
+            p = f"layers.{l}."
+            w[p + "input_layernorm.weight"] = torch.ones(H, device=device)
+            w[p + "post_attention_layernorm.weight"] = torch.ones(H, device=device)
+            w[p + "self_attn.q_proj.weight"] = rn(Hq * D, H)
+            w[p + "self_attn.k_proj.weight"] = rn(Hkv * D, H)
+            w[p + "self_attn.v_proj.weight"] = rn(Hkv * D, H)
+            w[p + "self_attn.q_proj.bias"] = rn(Hq * D)
+            w[p + "self_attn.k_proj.bias"] = rn(Hkv * D)
+            w[p + "self_attn.v_proj.bias"] = rn(Hkv * D)
+            w[p + "self_attn.o_proj.weight"] = rn(H, Hq * D)
+            w[p + "mlp.gate_proj.weight"] = rn(I, H)
+            w[p + "mlp.up_proj.weight"] = rn(I, H)
+            w[p + "mlp.down_proj.weight"] = rn(H, I)
+        return cls(cfg, w, device)
+
+    @classmethod
+    def from_qwen2_model(cls, qwen2_model, device) -> "QwenBackboneB200":
+        """From a transformers `Qwen2Model` (e.g. the reference's `UniGen.llm.model`)."""
+        c = qwen2_model.config
+        cfg = QwenConfig(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                         num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
+                         num_key_value_heads=c.num_key_value_heads,
+                         head_dim=getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads,
+                         vocab_size=c.vocab_size, rope_theta=_rope_theta(c), rms_norm_eps=c.rms_norm_eps)
+        return cls(cfg, dict(qwen2_model.state_dict()), device)
+
+    # -------------------------------------------------------------------------------------------
+    def _rope(self, L: int):
+        if L not in self._rope_cache:
+            D = self.cfg.head_dim
+            inv = 1.0 / (self.cfg.rope_theta ** (torch.arange(0, D, 2, dtype=torch.float32, device=self.device) / D))
+            fr = torch.outer(torch.arange(L, dtype=torch.float32, device=self.device), inv)      # positions arange(L)
+            self._rope_cache[L] = (fr.cos().contiguous(), fr.sin().contiguous())
+        return self._rope_cache[L]
+
+    def embed_tokens(self, token_ids: torch.Tensor) -> torch.Tensor:
+        """int64 [B,L] -> fp32 residual stream [B,L,H]."""
+        B, L = token_ids.shape
+        return ops.embed_rows(self.embed, token_ids.contiguous()).view(B, L, self.cfg.hidden_size)
+
+    def forward(self, x: torch.Tensor, pad_len: torch.Tensor, soi_idx: torch.Tensor, rows: Optional[slice] = None) -> torch.Tensor:
+        """x: fp32 [B,L,H] embeddings (consumed as the residual stream, modified in place).
+        Returns the final-norm hidden states, bf16 [B,L,H] (or [B,rows,H] when `rows` is given)."""
+        cfg = self.cfg
+        B, L, H = x.shape
+        Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        M = B * L
+        x2 = x.view(M, H)
+        cos, sin = self._rope(L)
+        scale = D ** -0.5
+        delta = None
+        for ly in self.layers:
+            h = ops.add_rmsnorm(x2, ly["ln1"], cfg.rms_norm_eps, delta)
+            qkv = F.linear(h, ly["wqkv"], ly["bqkv"])
+            ops.rope_qk_(qkv, cos, sin, L, Hq, Hkv, D)
+            q = qkv[:, : Hq * D].view(B, L, Hq, D)
+            k = qkv[:, Hq * D: (Hq + Hkv) * D].view(B, L, Hkv, D)
+            v = qkv[:, (Hq + Hkv) * D:].view(B, L, Hkv, D)
+            ev = self.attn_events
+            if ev is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            a = ops.omni_attention(q, k, v, pad_len, soi_idx, scale)
+            if ev is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                ev.append((e0, e1))
+            o = F.linear(a.view(M, Hq * D), ly["wo"])
+            h = ops.add_rmsnorm(x2, ly["ln2"], cfg.rms_norm_eps, o)
+            act = ops.swiglu(F.linear(h, ly["wgu"]))
+            delta = F.linear(act, ly["wd"])
+        hn = ops.add_rmsnorm(x2, self.final_norm, cfg.rms_norm_eps, delta).view(B, L, H)
+        return hn if rows is None else hn[:, rows]
+
+    def codebook_logits(self, hidden_img: torch.Tensor, text_vocab_size: int, V: int) -> torch.Tensor:
+        """bf16 [B,N,H] -> bf16 [B,N,V]: tied LM head restricted to rows [text_vocab, text_vocab+V)."""
+        return F.linear(hidden_img, self.embed[text_vocab_size: text_vocab_size + V])
+
+
+def _rope_theta(c) -> float:
+    t = getattr(c, "rope_theta", None)
+    if t is None:
+        rp = getattr(c, "rope_parameters", None) or {}
+        t = rp.get("rope_theta", 1000000.0)
+    return float(t)

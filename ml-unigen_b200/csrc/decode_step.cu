@@ -318,13 +318,17 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
     // =============================================================== consumers (256 threads)
     int stage = 0;
     uint32_t phase = 0;
+    int pending_sel = -1;            // thread 0: image whose last row this CTA published (checked one barrier later)
     while (true) {
         mbar_wait(&c->full[stage], phase);
         const int task = c->task[stage];
-        if (task == -1) break;
-        if (task <= -2) {
+        if (tid == 0) { c->sel_b = pending_sel; pending_sel = -1; }
+        if (task < 0) {                                            // sentinel (-1) or SELECT(b) (<= -2)
             consumer_bar();
             if (tid == 0) mbar_arrive(&c->empty[stage]);
+            const int sb = c->sel_b;
+            if (sb >= 0) select_phase(a, sb, c, keys, tid, nullptr);
+            if (task == -1) break;
             select_phase(a, -2 - task, c, keys, tid, nullptr);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
             continue;
@@ -332,16 +336,16 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
         const long long row = task;
         const int b = (int)(row / N);
         const uint64_t rowg = (uint64_t)(a.batch_offset + b) * (uint64_t)N + (uint64_t)(row - (long long)b * N);
+        const uint8_t* srow = ring + (size_t)stage * kStageBytes;   // stays valid until this row is published
 
         // ---- shared -> registers: 16 consecutive logits per chunk, two 16-byte halves in
         //      swapped order for threads 4..7 of each octet so LDS.128 is bank-conflict free
         uint32_t xb[kChunks * 8];
         {
-            const uint8_t* src = ring + (size_t)stage * kStageBytes;
             const int sw = (tid >> 2) & 1;
 #pragma unroll
             for (int ch = 0; ch < kChunks; ++ch) {
-                const uint8_t* p = src + ((size_t)ch * kConsumers + tid) * (kVec * 2);
+                const uint8_t* p = srow + ((size_t)ch * kConsumers + tid) * (kVec * 2);
                 uint4 h0 = *reinterpret_cast<const uint4*>(p + 16 * sw);
                 uint4 h1 = *reinterpret_cast<const uint4*>(p + 16 * (sw ^ 1));
                 uint4 lo = sw ? h1 : h0, hi = sw ? h0 : h1;
@@ -382,8 +386,12 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
             }
             if (lane == 0) { c->red_max[warp] = fmx; c->red_min[warp] = fmn; }
         }
-        consumer_bar();                                            // (1) ring slot fully read
-        if (tid == 0) { mbar_arrive(&c->empty[stage]); c->cand_cnt = 0; }
+        consumer_bar();                                            // (1)
+        {
+            const int sb = c->sel_b;                               // image completed by this CTA's previous row?
+            if (sb >= 0) select_phase(a, sb, c, keys, tid, nullptr);
+        }
+        if (tid == 0) c->cand_cnt = 0;
         float m = c->red_max[0], mn = c->red_min[0];
 #pragma unroll
         for (int w = 1; w < 8; ++w) { m = fmaxf(m, c->red_max[w]); mn = fminf(mn, c->red_min[w]); }
@@ -444,24 +452,32 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
                 }
             }
         } else {
-            // conservative filter: an element can reach ratio >= 1/16 only if coarse <= 256*16*p_i
+            // Conservative candidate filter, two elements per step, no branches: an element can reach the
+            // ratio 1/16 only if coarse <= 256*16*p_i.  T = rne(K*e) sits in the low mantissa bits of
+            // fma(K, e, 2^23); with 16-bit fields, (T + 0x8000 - coarse) has bit 15 set iff coarse <= T.
             const float K = __fdividef(kFilterK, S);
+            const float2 K2 = make_float2(K, K), magic2 = make_float2(8388608.0f, 8388608.0f);
 #pragma unroll
             for (int ch = 0; ch < kChunks; ++ch) {
                 const int i0 = (ch * kConsumers + tid) * kVec;
                 ug::u32x4 cb = ug::noise_call((uint32_t)(i0 >> 4), ug::kKindCoarse, rowg, a.seed, a.offset);
                 uint32_t cw[4] = {cb.x, cb.y, cb.z, cb.w};
+                uint32_t flags = 0;
 #pragma unroll
-                for (int k = 0; k < kVec; ++k) {
-                    float fb = __uint_as_float(__byte_perm(cw[k >> 2], 0x4b000000u, 0x7650u + (k & 3)));
-                    float thr = __fmaf_rn(K, e[ch * kVec + k], 8388608.0f);
-                    if (fb <= thr) {
-                        int s = atomicAdd(&c->cand_cnt, 1);
-                        if (s < kCandMax) {
-                            c->cand[s] = (uint32_t)(i0 + k) | ((__float_as_uint(fb) & 0xffu) << 16);
-                            c->cand_e[s] = e[ch * kVec + k];
-                        }
-                    }
+                for (int pr = 0; pr < kVec / 2; ++pr) {
+                    const float2 t2 = __ffma2_rn(K2, make_float2(e[ch * kVec + 2 * pr], e[ch * kVec + 2 * pr + 1]), magic2);
+                    const uint32_t tp = __byte_perm(__float_as_uint(t2.x), __float_as_uint(t2.y), 0x5410);
+                    const uint32_t cp = __byte_perm(cw[pr >> 1], 0u, (pr & 1) ? 0x4342 : 0x4140);   // [c0,0,c1,0]
+                    const uint32_t d = tp + 0x80008000u - cp;
+                    flags = (flags >> 1) | (d & 0x80008000u);
+                }
+                // bit p: element 2p, bit 16+p: element 2p+1 of this chunk (rare: ~0.2 candidates per thread)
+                while (flags) {
+                    const int bit = __ffs(flags) - 1;
+                    flags &= flags - 1;
+                    const int k = (bit < 16) ? 2 * bit : 2 * (bit - 16) + 1;
+                    const int s = atomicAdd(&c->cand_cnt, 1);
+                    if (s < kCandMax) c->cand[s] = (uint32_t)(i0 + k);
                 }
             }
             consumer_bar();                                        // (3)
@@ -469,10 +485,15 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
             need_full = cnt > kCandMax || a.force_full_race != 0;
             const int lim = cnt < kCandMax ? cnt : kCandMax;
             for (int s = tid; s < lim; s += kConsumers) {
-                const uint32_t ci = c->cand[s];
-                const int i = (int)(ci & 0xffffu);
-                const float q = ug::race_q_from_coarse(ci >> 16, (uint32_t)i, rowg, a.seed, a.offset);
-                const float p = __fdiv_rn(c->cand_e[s], S);
+                const int i = (int)c->cand[s];
+                // the logit is still in the ring slot; e_i is recomputed with the same IEEE operations
+                uint32_t xbits = *reinterpret_cast<const uint16_t*>(srow + 2 * i);
+                if (kCfg) xbits = ug::cfg_mix_bits(xbits, *reinterpret_cast<const uint16_t*>(srow + kRowBytes + 2 * i), a.guidance);
+                const float d = __fadd_rn(__uint_as_float(xbits << 16), -m);
+                const float ei = fast ? ug::expf_fast(d) : ug::expf_exact(d);
+                const ug::u32x4 cb = ug::noise_call((uint32_t)(i >> 4), ug::kKindCoarse, rowg, a.seed, a.offset);
+                const float q = ug::race_q_from_coarse(ug::coarse_byte(cb, (uint32_t)i & 15u), (uint32_t)i, rowg, a.seed, a.offset);
+                const float p = __fdiv_rn(ei, S);
                 const float r = __fdiv_rn(p, q);
                 best_merge(best, r, p, i);
             }
@@ -499,18 +520,17 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
                     race_eval_exact(e[ch * kVec + k], S, ug::coarse_byte(cb, k), i0 + k, rowg, a.seed, a.offset, best);
             }
         }
-        // ---- publish the row; the CTA that completes image b runs its mask selection
+        // ---- publish the row (the ring slot is free now).  Whether this row completed image b is known
+        //      only when the device-scope atomic returns; the CTA acts on it after its next barrier.
         if (tid == 0) {
+            mbar_arrive(&c->empty[stage]);
             a.sampled[row] = best.i;                               // models/unigen.py:419-422
             a.psel[row] = best.p;                                  // models/unigen.py:429-430
             if (a.rowsum_out) a.rowsum_out[row] = S;
             __threadfence();
             const unsigned old = atomicAdd(&a.counters[b], 1u);
-            c->sel_b = (old == (unsigned)(N - 1)) ? b : -1;
+            pending_sel = (old == (unsigned)(N - 1)) ? b : -1;
         }
-        consumer_bar();                                            // (5)
-        const int sb = c->sel_b;
-        if (sb >= 0) select_phase(a, sb, c, keys, tid, nullptr);
         if (++stage == stages) { stage = 0; phase ^= 1u; }
     }
 }

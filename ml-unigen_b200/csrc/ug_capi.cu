@@ -7,6 +7,7 @@
 #include "unigen_b200.h"
 #include "decode_step.h"
 #include "omni_attention.h"
+#include "backbone_ops.h"
 
 float* ugk_debug_rowsum_out();
 int ugk_debug_force_full_race();
@@ -197,3 +198,46 @@ extern "C" void ug_debug_set_force_full_race(int on) { g_force_full_race = on; }
 int ugk_debug_force_full_race() { return g_force_full_race; }
 
 extern "C" void ug_debug_set_attn_dump(float* p) { ugk::set_attn_debug(p); }
+
+// ---- row-wise backbone kernels ---------------------------------------------------------------------
+extern "C" int ug_add_rmsnorm(float* x, const void* delta_bf16, const void* weight_bf16, void* out_bf16,
+                              int64_t M, int H, float eps, void* stream)
+{
+    if (!x || !weight_bf16 || !out_bf16) return fail(UG_ERR_NULL, "ug_add_rmsnorm: x, weight, out are required");
+    if (M < 1 || H % 256 != 0 || H > 8192) return fail(UG_ERR_SHAPE, "ug_add_rmsnorm: M=%lld H=%d unsupported (H %% 256 == 0, H <= 8192)", (long long)M, H);
+    if (!aligned16(x) || !aligned16(delta_bf16) || !aligned16(weight_bf16) || !aligned16(out_bf16))
+        return fail(UG_ERR_ALIGN, "ug_add_rmsnorm: pointers must be 16-byte aligned");
+    cudaError_t e = ugk::launch_add_rmsnorm(x, delta_bf16, weight_bf16, out_bf16, M, H, eps, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_add_rmsnorm launch");
+    return UG_OK;
+}
+
+extern "C" int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, int64_t M, int L, int Hq, int Hkv, int D, void* stream)
+{
+    if (!qkv_bf16 || !cos || !sin) return fail(UG_ERR_NULL, "ug_rope_qk: null pointer");
+    if (M < 1 || L < 1 || D % 16 != 0 || Hq < 1 || Hkv < 1) return fail(UG_ERR_SHAPE, "ug_rope_qk: bad shape");
+    if (!aligned16(qkv_bf16) || !aligned16(cos) || !aligned16(sin)) return fail(UG_ERR_ALIGN, "ug_rope_qk: pointers must be 16-byte aligned");
+    cudaError_t e = ugk::launch_rope_qk(qkv_bf16, cos, sin, M, L, Hq, Hkv, D, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_rope_qk launch");
+    return UG_OK;
+}
+
+extern "C" int ug_swiglu(const void* gate_up_bf16, void* act_bf16, int64_t M, int I, void* stream)
+{
+    if (!gate_up_bf16 || !act_bf16) return fail(UG_ERR_NULL, "ug_swiglu: null pointer");
+    if (M < 1 || I % 8 != 0) return fail(UG_ERR_SHAPE, "ug_swiglu: bad shape");
+    if (!aligned16(gate_up_bf16) || !aligned16(act_bf16)) return fail(UG_ERR_ALIGN, "ug_swiglu: pointers must be 16-byte aligned");
+    cudaError_t e = ugk::launch_swiglu(gate_up_bf16, act_bf16, M, I, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_swiglu launch");
+    return UG_OK;
+}
+
+extern "C" int ug_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64_t M, int H, int64_t vocab, void* stream)
+{
+    if (!x || !table_bf16 || !tokens) return fail(UG_ERR_NULL, "ug_embed_rows: null pointer");
+    if (M < 1 || H % 8 != 0 || vocab < 1) return fail(UG_ERR_SHAPE, "ug_embed_rows: bad shape");
+    if (!aligned16(x) || !aligned16(table_bf16)) return fail(UG_ERR_ALIGN, "ug_embed_rows: pointers must be 16-byte aligned");
+    cudaError_t e = ugk::launch_embed_rows(x, table_bf16, tokens, M, H, vocab, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_embed_rows launch");
+    return UG_OK;
+}

@@ -148,14 +148,9 @@ struct u32x4 { uint32_t x, y, z, w; };
 
 UG_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
 {
-#if defined(__CUDA_ARCH__)
-    lo = a * b;
-    hi = __umulhi(a, b);
-#else
-    uint64_t p = (uint64_t)a * b;
+    const uint64_t p = (uint64_t)a * b;                    // one IMAD.WIDE.U32
     lo = (uint32_t)p;
     hi = (uint32_t)(p >> 32);
-#endif
 }
 
 UG_HD u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1)

@@ -131,3 +131,59 @@ def omni_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_len: t
         out.stride(0), out.stride(1), out.stride(2), _stream())
     _lib.check(rc)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# row-wise kernels of the decoder layer
+def add_rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, delta: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x fp32 [M,H] residual stream (updated in place with `delta` bf16 [M,H] when given);
+    returns bf16 [M,H] = weight * rmsnorm(x)."""
+    _need_cuda(x, weight, delta)
+    M, H = x.shape
+    if x.dtype != torch.float32 or not x.is_contiguous() or weight.dtype != torch.bfloat16:
+        raise ValueError("x must be contiguous fp32 [M,H], weight bf16 [H]")
+    if delta is not None and (delta.dtype != torch.bfloat16 or tuple(delta.shape) != (M, H) or not delta.is_contiguous()):
+        raise ValueError("delta must be contiguous bf16 [M,H]")
+    if out is None:
+        out = torch.empty(M, H, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().ug_add_rmsnorm(_ptr(x), _ptr(delta), _ptr(weight), _ptr(out), M, H, float(eps), _stream()))
+    return out
+
+
+def rope_qk_(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, L: int, Hq: int, Hkv: int, D: int) -> torch.Tensor:
+    """In-place RoPE on the q and k heads of the fused qkv activation bf16 [M,(Hq+2Hkv)*D]."""
+    _need_cuda(qkv, cos, sin)
+    M = qkv.shape[0]
+    if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous() or qkv.shape[1] != (Hq + 2 * Hkv) * D:
+        raise ValueError("qkv must be contiguous bf16 [M,(Hq+2Hkv)*D]")
+    if cos.dtype != torch.float32 or tuple(cos.shape) != (L, D // 2) or not cos.is_contiguous() or sin.shape != cos.shape:
+        raise ValueError("cos/sin must be contiguous fp32 [L, D/2]")
+    _lib.check(_lib.lib().ug_rope_qk(_ptr(qkv), _ptr(cos), _ptr(sin), M, L, Hq, Hkv, D, _stream()))
+    return qkv
+
+
+def swiglu(gate_up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 [M,2I] = [gate | up] -> bf16 [M,I] = silu(gate) * up."""
+    _need_cuda(gate_up)
+    M, I2 = gate_up.shape
+    if gate_up.dtype != torch.bfloat16 or not gate_up.is_contiguous() or I2 % 16:
+        raise ValueError("gate_up must be contiguous bf16 [M,2I]")
+    if out is None:
+        out = torch.empty(M, I2 // 2, dtype=torch.bfloat16, device=gate_up.device)
+    _lib.check(_lib.lib().ug_swiglu(_ptr(gate_up), _ptr(out), M, I2 // 2, _stream()))
+    return out
+
+
+def embed_rows(table: torch.Tensor, tokens: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """table bf16 [vocab,H], tokens int64 [M] -> fp32 [M,H]."""
+    _need_cuda(table, tokens)
+    vocab, H = table.shape
+    tokens = tokens.reshape(-1)
+    if table.dtype != torch.bfloat16 or not table.is_contiguous() or tokens.dtype != torch.int64 or not tokens.is_contiguous():
+        raise ValueError("table must be contiguous bf16, tokens contiguous int64")
+    M = tokens.numel()
+    if out is None:
+        out = torch.empty(M, H, dtype=torch.float32, device=table.device)
+    _lib.check(_lib.lib().ug_embed_rows(_ptr(out), _ptr(table), _ptr(tokens), M, H, vocab, _stream()))
+    return out

@@ -1,0 +1,160 @@
+"""`UniGenB200.t2i_generate` -- drop-in for `UniGen.t2i_generate` (apple/ml-unigen
+models/unigen.py:344-455): same keyword arguments, same return value (int64 [B,N] codebook ids of the
+last step), different machinery:
+
+  reference (per step)                                   this module (per step)
+  ----------------------------------------------------   ---------------------------------------------
+  cat(prefix, image, suffix) embeddings                   image rows re-embedded in place (ug_embed_rows)
+  Qwen2Model with dense fp32 [B,1,L,L] mask, SDPA         QwenBackboneB200: tcgen05 omni attention on (P_b,S_b)
+  lm_head over L x 159867, then slice [N x 8192]          codebook-only head GEMM -> dense bf16 [B,N,V]
+  CFG mix, softmax, multinomial (host sync), gather,      ONE launch of ug_decode_step_bf16 (CFG, softmax,
+  where, log, uniform_, sort, gather, <, where (~12       exponential race, confidence, k-th smallest,
+  launches, 8 passes over a 537 MB fp32 tensor)           re-masking; logits read once)
+  H2D copies of mask_len / tensor([1]) each step          no host<->device traffic inside the loop
+
+The MaskGIT schedule arithmetic (ratio, `noise_schedule(torch.tensor(ratio))`, floor(N*mask_ratio),
+the compounding temperature of unigen.py:444) is evaluated on the host exactly as the reference does.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from . import ops, prompting
+from .backbone import QwenBackboneB200, QwenConfig
+from .sampling import cosine_schedule
+
+
+class UniGenB200:
+    def __init__(self, backbone: QwenBackboneB200, *, codebook_size: int = 8192, mask_token_id: Optional[int] = None,
+                 pad_id: int = prompting.QWEN_PAD_ID, soi_id: int = prompting.QWEN_SOI_ID):
+        self.backbone = backbone
+        self.codebook_size = codebook_size
+        # models/unigen.py:92 -- mask_token_id = vocab_size - 1 when no separate image head exists
+        self.mask_token_id = backbone.cfg.vocab_size - 1 if mask_token_id is None else mask_token_id
+        self.pad_id, self.soi_id = pad_id, soi_id
+        self.device = backbone.device
+        self._ws = {}
+        self.last_sel_prob = None
+        self.decode_events = None      # bench hook: (start, end) CUDA events of every decode-step launch
+
+    # reference-style constructors -------------------------------------------------------------
+    @classmethod
+    def random_init(cls, device, cfg: Optional[QwenConfig] = None, seed: int = 0, **kw) -> "UniGenB200":
+        return cls(QwenBackboneB200.random_init(cfg or QwenConfig(), device, seed=seed), **kw)
+
+    @classmethod
+    def from_reference(cls, ref_unigen, device) -> "UniGenB200":
+        """From an instance of the reference's `UniGen` (its `llm` is a transformers Qwen2ForCausalLM)."""
+        bb = QwenBackboneB200.from_qwen2_model(ref_unigen.llm.model, device)
+        return cls(bb, codebook_size=getattr(ref_unigen, "img_output_size", 8192),
+                   mask_token_id=int(ref_unigen.config.mask_token_id))
+
+    # ---------------------------------------------------------------------------------------------
+    def _workspace(self, B, N, V):
+        key = (B, N, V)
+        if key not in self._ws:
+            self._ws[key] = ops.DecodeWorkspace(B, N, V, self.device)
+        return self._ws[key]
+
+    def _mask_params(self, input_ids, attention_mask, validate: bool):
+        if attention_mask is not None and attention_mask.dim() == 4:
+            P, S = prompting.omni_mask_params_from_dense(attention_mask)
+            if validate and not bool(prompting.dense_mask_matches(attention_mask, P, S)):
+                raise ValueError("attention_mask is not an omni mask of create_attention_mask_predict_next("
+                                 "rm_pad_in_image=True); other masks are outside this path")
+            return P.contiguous(), S.contiguous()
+        if attention_mask is not None:
+            raise NotImplementedError("2-D (use_causal_mask) masks are not part of the T2I decoding path")
+        return prompting.omni_mask_params(input_ids, self.pad_id, self.soi_id)
+
+    @torch.no_grad()
+    def t2i_generate(
+        self,
+        input_ids: Optional[torch.LongTensor] = None,
+        uncond_input_ids: Optional[torch.LongTensor] = None,
+        input_embeddings: Optional[torch.Tensor] = None,
+        uncond_input_embeddings: Optional[torch.Tensor] = None,
+        attention_mask: Optional[torch.Tensor] = None,
+        temperature: float = 1.0,
+        timesteps: int = 18,
+        guidance_scale: int = 0,
+        noise_schedule: Callable = cosine_schedule,
+        generator: Optional[torch.Generator] = None,
+        image_token_num_per_image: int = 256,
+        text_vocab_size: int = 151936,
+        **kwargs,
+    ):
+        """See models/unigen.py:344-359 for the arguments.  Extra keyword arguments understood here:
+        `batch_offset` (global index of image 0: sharding-invariant noise), `validate_mask` (default True),
+        `philox_seed` / `philox_offset` (override the generator-derived stream)."""
+        if input_embeddings is not None or uncond_input_embeddings is not None:
+            raise NotImplementedError("precomputed input_embeddings are not used by any T2I caller of the reference")
+        if not input_ids.is_cuda:
+            input_ids = input_ids.to(self.device, non_blocking=True)
+        N, V = image_token_num_per_image, self.codebook_size
+        bb, mask_id = self.backbone, self.mask_token_id
+        B, L = input_ids.shape
+        use_cfg = guidance_scale > 1                                    # models/unigen.py:382 (sic: > 1, not > 0)
+        ids_img = input_ids[:, -(N + 1):-1].clone().contiguous()        # unigen.py:367
+        tokens = input_ids.clone()
+        if use_cfg:
+            if uncond_input_ids is None:
+                raise ValueError("guidance_scale > 1 needs uncond_input_ids")
+            tokens = torch.cat([tokens, uncond_input_ids.to(self.device)], 0)
+        if attention_mask is not None and attention_mask.shape[0] != tokens.shape[0]:
+            raise ValueError("attention_mask batch must match cond (+ uncond) batch")
+        P, S = self._mask_params(tokens, attention_mask, kwargs.get("validate_mask", True))
+
+        gen = generator
+        if "philox_seed" in kwargs:
+            seed, base_offset = int(kwargs["philox_seed"]), int(kwargs.get("philox_offset", 0))
+        else:
+            if gen is None:
+                gen = torch.cuda.default_generators[self.device.index or 0]
+            seed, base_offset = gen.initial_seed(), (gen.get_offset() if gen.device.type == "cuda" else 0)
+            if gen.device.type == "cuda":
+                gen.set_offset(base_offset + 4 * ((timesteps + 3) // 4))   # consume a distinct slice of the stream
+        batch_offset = int(kwargs.get("batch_offset", 0))
+        trace = kwargs.get("trace")
+
+        ws = self._workspace(B, N, V)
+        sampled = torch.empty(B, N, dtype=torch.int64, device=self.device)
+        masking = torch.empty(B, N, dtype=torch.uint8, device=self.device)
+        sel_prob = torch.empty(B, N, dtype=torch.float32, device=self.device)
+        img_rows = slice(L - N - 1, L - 1)
+        temp = float(temperature)
+        for step in range(timesteps):
+            # tokens of the image block: mask id stays, codebook id c becomes c + text_vocab (unigen.py:451)
+            img_tok = torch.where(ids_img == mask_id, ids_img, ids_img + text_vocab_size)
+            tokens[:B, img_rows] = img_tok
+            if use_cfg:
+                tokens[B:, img_rows] = img_tok
+            x = bb.embed_tokens(tokens)
+            hidden = bb.forward(x, P, S, rows=img_rows)                  # bf16 [B(2B), N, H]
+            logits = bb.codebook_logits(hidden, text_vocab_size, V)      # bf16 [B(2B), N, V]
+            ratio = 1.0 * (step + 1) / timesteps                        # unigen.py:425
+            mask_ratio = noise_schedule(torch.tensor(ratio))             # unigen.py:426 (0-d CPU tensor)
+            cap = int((N * mask_ratio).floor().item())                   # unigen.py:436 (host scalar, no device sync)
+            temp = temp * (1.0 - ratio)                                  # unigen.py:444
+            ev = self.decode_events
+            if ev is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            ops.decode_step(logits[:B], ids_img, mask_token_id=mask_id, mask_len_cap=cap, temperature=temp,
+                            workspace=ws, sampled_out=sampled, mask_out=masking, sel_prob_out=sel_prob,
+                            uncond_logits=logits[B:] if use_cfg else None, guidance_scale=float(guidance_scale),
+                            seed=seed, offset=base_offset + step, batch_offset=batch_offset)
+            if ev is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                ev.append((e0, e1))
+            if trace is not None:                                        # test hook: what each step saw and produced
+                trace.append(dict(logits=logits.clone(), cap=cap, temperature=temp, offset=base_offset + step,
+                                  ids_after=ids_img.clone(), sampled=sampled.clone(), masking=masking.clone()))
+        self.last_sel_prob = sel_prob
+        return sampled
+
+    # callers in the reference use model(...) only through t2i_generate on this path
+    generate_images = t2i_generate

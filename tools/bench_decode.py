@@ -26,7 +26,7 @@ def main():
     out = []
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for scale in (4.0, 0.02):
-        for B in (1, 2, 4, 8, 16, 32, 64, 128):
+        for B in [int(b) for b in os.environ.get("BS", "1,2,4,8,16,32,64,128").split(",")]:
             g = torch.Generator(device=dev).manual_seed(0)
             logits = (scale * torch.randn(B, N, V, device=dev, generator=g)).bfloat16()
             ws = ops.DecodeWorkspace(B, N, V, dev)
