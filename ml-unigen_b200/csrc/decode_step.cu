@@ -471,11 +471,12 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
                     const uint32_t d = tp + 0x80008000u - cp;
                     flags = (flags >> 1) | (d & 0x80008000u);
                 }
-                // bit p: element 2p, bit 16+p: element 2p+1 of this chunk (rare: ~0.2 candidates per thread)
+                // after kVec/2 = 8 shifts pair p sits at bit 8+p (even element 2p) and bit 24+p (odd element 2p+1)
+                // (rare: ~0.2 candidates per thread)
                 while (flags) {
                     const int bit = __ffs(flags) - 1;
                     flags &= flags - 1;
-                    const int k = (bit < 16) ? 2 * bit : 2 * (bit - 16) + 1;
+                    const int k = (bit < 16) ? 2 * (bit - (16 - kVec / 2)) : 2 * (bit - (32 - kVec / 2)) + 1;
                     const int s = atomicAdd(&c->cand_cnt, 1);
                     if (s < kCandMax) c->cand[s] = (uint32_t)(i0 + k);
                 }
