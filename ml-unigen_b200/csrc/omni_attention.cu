@@ -6,14 +6,18 @@
 // is never materialised: it is the closed form of two integers per sequence (pad_len P_b,
 // soi_idx S_b) and fully masked KV tiles are skipped.
 //
-// One CTA = one 128-row query tile of one (batch, q-head); 192 threads:
-//   warps 0-3  softmax / correction / epilogue: thread r owns query row r (TMEM lane r)
-//   warp  4    TMA producer: Q once, then K_j / V_j tiles (2-deep rings), SWIZZLE_128B boxes
-//   warp  5    MMA issuer (one elected lane): S_j = Q K_j^T and O += P_j V_j with tcgen05.mma
+// One CTA = 256 query rows (two 128-row tiles A and B) of one (batch, q-head); 320 threads:
+//   warps 0-3  softmax / correction / epilogue of tile A: thread r owns query row r (TMEM lane r)
+//   warps 4-7  the same for tile B
+//   warp  8    TMA producer: Q_A, Q_B once, then K_t / V_t tiles (2-deep rings), SWIZZLE_128B boxes
+//   warp  9    MMA issuer (one elected lane): S_x = Q_x K_t^T and O_x += P_x V_t with tcgen05.mma
 //              (kind::f16, bf16 x bf16 -> fp32, M=128 N=128 K=16), accumulators in TMEM
-// TMEM columns: S ping [0,128), S pong [128,256), O [256,384).
-// S is double buffered so that QK^T of tile j+1 runs on the tensor core while the softmax warps
-// work on tile j; P_j goes through shared memory in the K-major SWIZZLE_128B UMMA layout.
+// TMEM columns: S_A [0,128), S_B [128,256), O_A [256,384), O_B [384,512).  P_x (bf16 pairs) overwrites the
+// first 64 columns of S_x and is the A operand of the second GEMM straight from tensor memory, so the
+// probabilities never touch shared memory.  The two tiles ping-pong: while warpgroup A is in its softmax
+// the tensor core runs the GEMMs of tile B and vice versa; the issue order per kv tile is
+// PV_A(t), QK_A(t+1), PV_B(t), QK_B(t+1).  Row maxima are rescaled lazily (only when the true max moved by
+// more than 2^8), which is exact because O, l and P always share the same reference max.
 // GQA: the 6 query heads of a KV head read the same K/V tiles (L2 hits); nothing is expanded.
 #include <cuda_runtime.h>
 #include <cuda.h>
@@ -29,28 +33,10 @@ namespace ugk {
 constexpr int kBM = 128;             // query rows per CTA
 constexpr int kBN = 128;             // kv rows per tile
 constexpr int kD = 128;              // head dim
-constexpr int kAttnThreads = 192;
 constexpr uint32_t kTileBytes = kBM * kD * 2;          // 32 KB: one [128 x 128] bf16 tile (two 64-wide swizzle panels)
 constexpr uint32_t kPanelBytes = kTileBytes / 2;       // 16 KB: [128 rows x 64 cols] panel, 128-byte rows
 constexpr int kKVStages = 2;
 
-// shared memory map (dynamic, 1024-byte aligned)
-constexpr uint32_t kOffQ = 0;
-constexpr uint32_t kOffK = kOffQ + kTileBytes;
-constexpr uint32_t kOffV = kOffK + kKVStages * kTileBytes;
-constexpr uint32_t kOffP = kOffV + kKVStages * kTileBytes;
-constexpr uint32_t kOffBar = kOffP + kTileBytes;
-constexpr uint32_t kAttnSmem = kOffBar + 256 + 1024;   // + barriers + alignment slack
-
-struct AttnBars {
-    uint64_t q_full;
-    uint64_t k_full[kKVStages], k_empty[kKVStages];
-    uint64_t v_full[kKVStages], v_empty[kKVStages];
-    uint64_t s_full[2], s_empty[2];
-    uint64_t p_full;
-    uint64_t pv_done;
-    uint32_t tmem_base;
-};
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -170,36 +156,84 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn_major, 
 struct AttnParams {
     AttnArgs a;
     float scale_log2;       // scale * log2(e)
-    int n_qtiles;
+    int n_qpairs;           // CTAs along the sequence: 256 query rows each
     float* dbg;             // optional: dumps S and P of (b=0, h=0, q tile 0, kv tile 0)
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+// TS form: A operand (P, bf16 pairs) read from tensor memory, B from shared memory
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+// kv tile range [t0, t1) needed by the query rows [i0, i1) under the omni mask (P = pad_len, S = soi_idx)
+__device__ __forceinline__ void kv_range(int i0, int i1, int P, int S, int L, int& t0, int& t1)
+{
+    const int jlo = (i0 < P) ? 0 : P;
+    const int jhi = (i1 > S) ? L : i1;
+    t0 = jlo / kBN;
+    t1 = (jhi + kBN - 1) / kBN;
+}
+
+// Shared memory: Q tile A | Q tile B | K ring (2) | V ring (2) | barriers.  P lives in tensor memory.
+constexpr uint32_t kOff2QA = 0;
+constexpr uint32_t kOff2QB = kOff2QA + kTileBytes;
+constexpr uint32_t kOff2K = kOff2QB + kTileBytes;
+constexpr uint32_t kOff2V = kOff2K + kKVStages * kTileBytes;
+constexpr uint32_t kOff2Bar = kOff2V + kKVStages * kTileBytes;
+constexpr uint32_t kAttn2Smem = kOff2Bar + 256 + 1024;
+constexpr int kAttn2Threads = 320;           // 2 softmax warpgroups (one per query tile) + TMA warp + MMA warp
+constexpr float kRescaleTau = 8.0f;          // keep a stale row max until the true max moved by > 2^8 (exact, lazy rescaling)
+
+struct Attn2Bars {
+    uint64_t q_full;
+    uint64_t k_full[kKVStages], k_empty[kKVStages];
+    uint64_t v_full[kKVStages], v_empty[kKVStages];
+    uint64_t s_full[2];          // per query tile: S = Q K^T landed in TMEM (tcgen05.commit)
+    uint64_t p_full[2];          // per query tile: P written to TMEM by the 128 softmax threads
+    uint64_t o_done[2];          // per query tile: last P V accumulated
+    uint32_t tmem_base;
+};
+
+// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P_X aliases the first 64 columns of S_X
+// (bf16 pairs): the P chunk written after reading S chunk c only covers columns already consumed.
+__global__ void __launch_bounds__(kAttn2Threads, 1)
 omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const AttnParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    AttnBars* bars = reinterpret_cast<AttnBars*>(smem + kOffBar);
+    Attn2Bars* bars = reinterpret_cast<Attn2Bars*>(smem + kOff2Bar);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.a.L;
-    // heaviest tiles (image rows) first: reverse the q-tile index
-    const int qt = p.n_qtiles - 1 - (int)blockIdx.x;
+    const int qp = p.n_qpairs - 1 - (int)blockIdx.x;        // heaviest (image-row) tiles first
     const int h = blockIdx.y, b = blockIdx.z;
     const int hk = h / (p.a.Hq / p.a.Hkv);
-    const int i0 = qt * kBM;
-    const int i1 = min(i0 + kBM, L);
     int P = p.a.pad_len[b], S = p.a.soi_idx[b];
     P = max(0, min(P, L));
     S = max(P, min(S, L));
 
-    // kv range needed by this query tile (closed form of the omni mask)
-    const int jlo = (i0 < P) ? 0 : P;
-    const int jhi = (i1 > S) ? L : i1;
-    const int t0 = jlo / kBN;
-    const int t1 = (jhi + kBN - 1) / kBN;
-    const int n_tiles = t1 - t0;               // >= 1
+    // the two query tiles of this CTA and the kv tiles each of them needs
+    const int iA = qp * 2 * kBM, iB = iA + kBM;
+    const bool hasB = iB < L;
+    int tA0, tA1, tB0 = 0, tB1 = 0;
+    kv_range(iA, min(iA + kBM, L), P, S, L, tA0, tA1);
+    if (hasB) kv_range(iB, min(iB + kBM, L), P, S, L, tB0, tB1);
+    const int tU0 = hasB ? min(tA0, tB0) : tA0;
+    const int tU1 = hasB ? max(tA1, tB1) : tA1;
 
     if (tid == 0) {
         bar_init(&bars->q_full, 1);
@@ -207,12 +241,10 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             bar_init(&bars->k_full[s], 1); bar_init(&bars->k_empty[s], 1);
             bar_init(&bars->v_full[s], 1); bar_init(&bars->v_empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) { bar_init(&bars->s_full[s], 1); bar_init(&bars->s_empty[s], 128); }
-        bar_init(&bars->p_full, 128);
-        bar_init(&bars->pv_done, 1);
+        for (int x = 0; x < 2; ++x) { bar_init(&bars->s_full[x], 1); bar_init(&bars->p_full[x], 128); bar_init(&bars->o_done[x], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {       // TMEM: 512 columns (S ping, S pong, O) -- one CTA per SM, nobody else competes
+    if (warp == 8) {       // TMEM: all 512 columns (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&bars->tmem_base)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -222,200 +254,225 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // =========================================================== TMA producer
         if (lane == 0) {
-            bar_expect_tx(&bars->q_full, kTileBytes);
-            tma_load_4d(smem + kOffQ, &tm_q, &bars->q_full, 0, i0, h, b);
-            tma_load_4d(smem + kOffQ + kPanelBytes, &tm_q, &bars->q_full, 64, i0, h, b);
-            for (int j = 0; j < n_tiles; ++j) {
+            bar_expect_tx(&bars->q_full, hasB ? 2 * kTileBytes : kTileBytes);
+            tma_load_4d(smem + kOff2QA, &tm_q, &bars->q_full, 0, iA, h, b);
+            tma_load_4d(smem + kOff2QA + kPanelBytes, &tm_q, &bars->q_full, 64, iA, h, b);
+            if (hasB) {
+                tma_load_4d(smem + kOff2QB, &tm_q, &bars->q_full, 0, iB, h, b);
+                tma_load_4d(smem + kOff2QB + kPanelBytes, &tm_q, &bars->q_full, 64, iB, h, b);
+            }
+            for (int t = tU0; t < tU1; ++t) {
+                const int j = t - tU0;
                 const int s = j % kKVStages;
                 const uint32_t ph = (uint32_t)(j / kKVStages) & 1u;
-                const int j0 = (t0 + j) * kBN;
+                const int j0 = t * kBN;
                 bar_wait(&bars->k_empty[s], ph ^ 1u);
                 bar_expect_tx(&bars->k_full[s], kTileBytes);
-                tma_load_4d(smem + kOffK + s * kTileBytes, &tm_k, &bars->k_full[s], 0, j0, hk, b);
-                tma_load_4d(smem + kOffK + s * kTileBytes + kPanelBytes, &tm_k, &bars->k_full[s], 64, j0, hk, b);
+                tma_load_4d(smem + kOff2K + s * kTileBytes, &tm_k, &bars->k_full[s], 0, j0, hk, b);
+                tma_load_4d(smem + kOff2K + s * kTileBytes + kPanelBytes, &tm_k, &bars->k_full[s], 64, j0, hk, b);
                 bar_wait(&bars->v_empty[s], ph ^ 1u);
                 bar_expect_tx(&bars->v_full[s], kTileBytes);
-                tma_load_4d(smem + kOffV + s * kTileBytes, &tm_v, &bars->v_full[s], 0, j0, hk, b);
-                tma_load_4d(smem + kOffV + s * kTileBytes + kPanelBytes, &tm_v, &bars->v_full[s], 64, j0, hk, b);
+                tma_load_4d(smem + kOff2V + s * kTileBytes, &tm_v, &bars->v_full[s], 0, j0, hk, b);
+                tma_load_4d(smem + kOff2V + s * kTileBytes + kPanelBytes, &tm_v, &bars->v_full[s], 64, j0, hk, b);
             }
         }
-    } else if (warp == 5) {
-        // =========================================================== MMA issuer
+    } else if (warp == 9) {
+        // =========================================================== MMA issuer (one thread)
         if (lane == 0) {
             constexpr uint32_t idesc_qk = make_idesc(kBM, kBN, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);
-            const uint32_t q_addr = s_u32(smem + kOffQ), p_addr = s_u32(smem + kOffP);
-            auto issue_qk = [&](int j) {
-                const int s = j % kKVStages, sb = j & 1;
-                bar_wait(&bars->k_full[s], (uint32_t)(j / kKVStages) & 1u);
-                if (j >= 2) bar_wait(&bars->s_empty[sb], (uint32_t)((j >> 1) + 1) & 1u);
-                tc_fence_after();
-                const uint32_t k_addr = s_u32(smem + kOffK + s * kTileBytes);
+            const uint32_t qa_addr = s_u32(smem + kOff2QA), qb_addr = s_u32(smem + kOff2QB);
+            int np[2] = {0, 0};                              // P tiles consumed per query tile (phase of p_full)
+            auto in_range = [&](int x, int t) { return x == 0 ? (t >= tA0 && t < tA1) : (hasB && t >= tB0 && t < tB1); };
+            // S_x = Q_x K_t^T ; signals s_full[x]; the LAST QK of a kv tile also frees its K slot
+            auto issue_qk = [&](int x, int t) {
+                const int j = t - tU0, s = j % kKVStages;
+                const uint32_t k_addr = s_u32(smem + kOff2K + s * kTileBytes);
+                const uint32_t q_addr = x == 0 ? qa_addr : qb_addr;
 #pragma unroll
                 for (int k = 0; k < kD / 16; ++k) {
-                    // 16 bf16 along K = 32 bytes inside the 128-byte swizzle row; panel switch at k = 4
                     const uint32_t off = (uint32_t)(k >> 2) * kPanelBytes + (uint32_t)(k & 3) * 32u;
-                    tc_mma(tmem + (uint32_t)sb * 128u, desc_kmajor(q_addr + off), desc_kmajor(k_addr + off), idesc_qk, k > 0);
+                    tc_mma(tmem + (uint32_t)x * 128u, desc_kmajor(q_addr + off), desc_kmajor(k_addr + off), idesc_qk, k > 0);
                 }
-                tc_commit(&bars->k_empty[s]);
-                tc_commit(&bars->s_full[sb]);
+                tc_commit(&bars->s_full[x]);
+            };
+            auto qk_pair = [&](int t) {                      // both query tiles against kv tile t
+                const int j = t - tU0, s = j % kKVStages;
+                bar_wait(&bars->k_full[s], (uint32_t)(j / kKVStages) & 1u);
+                tc_fence_after();
+                return s;
             };
             bar_wait(&bars->q_full, 0);
-            issue_qk(0);
-            for (int j = 0; j < n_tiles; ++j) {
-                if (j + 1 < n_tiles) issue_qk(j + 1);
-                const int s = j % kKVStages;
-                bar_wait(&bars->p_full, (uint32_t)j & 1u);
-                bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u);
-                tc_fence_after();
-                const uint32_t v_addr = s_u32(smem + kOffV + s * kTileBytes);
+            // prologue: scores of the first kv tile
+            {
+                const int s = qk_pair(tU0);
+                if (in_range(0, tU0)) issue_qk(0, tU0);
+                if (in_range(1, tU0)) issue_qk(1, tU0);
+                tc_commit(&bars->k_empty[s]);
+            }
+            for (int t = tU0; t < tU1; ++t) {
+                const int j = t - tU0, s = j % kKVStages;
+                const bool next = t + 1 < tU1;
+                int sn = 0;
+                bool v_ready = false;
 #pragma unroll
-                for (int k = 0; k < kBN / 16; ++k) {
-                    const uint32_t a_off = (uint32_t)(k >> 2) * kPanelBytes + (uint32_t)(k & 3) * 32u;   // P: K-major
-                    const uint32_t b_off = (uint32_t)k * 16u * 128u;                                      // V: 16 kv rows
-                    tc_mma(tmem + 256u, desc_kmajor(p_addr + a_off), desc_mnmajor(v_addr + b_off), idesc_pv,
-                           (j > 0 || k > 0) ? 1u : 0u);
+                for (int x = 0; x < 2; ++x) {
+                    if (in_range(x, t)) {
+                        // O_x (+)= P_x V_t  once the softmax warpgroup x has written P_x
+                        bar_wait(&bars->p_full[x], (uint32_t)np[x] & 1u);
+                        if (!v_ready) { bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u); v_ready = true; }
+                        tc_fence_after();
+                        const uint32_t v_addr = s_u32(smem + kOff2V + s * kTileBytes);
+                        const int first_t = x == 0 ? tA0 : tB0;
+#pragma unroll
+                        for (int k = 0; k < kBN / 16; ++k)
+                            tc_mma_ts(tmem + 256u + (uint32_t)x * 128u, tmem + (uint32_t)x * 128u + (uint32_t)k * 8u,
+                                      desc_mnmajor(v_addr + (uint32_t)k * 16u * 128u), idesc_pv, (t > first_t || k > 0) ? 1u : 0u);
+                        ++np[x];
+                        const int last_t = (x == 0 ? tA1 : tB1) - 1;
+                        if (t == last_t) tc_commit(&bars->o_done[x]);
+                    }
+                    // scores of the next kv tile for the same query tile go right behind (keeps the tensor core busy
+                    // while the other warpgroup is still in its softmax)
+                    if (next) {
+                        if (x == 0) sn = qk_pair(t + 1);
+                        if (in_range(x, t + 1)) issue_qk(x, t + 1);
+                    }
                 }
+                if (!v_ready) { bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u); }
                 tc_commit(&bars->v_empty[s]);
-                tc_commit(&bars->pv_done);
+                if (next) tc_commit(&bars->k_empty[sn]);
             }
         }
     } else {
-        // =========================================================== softmax / correction / epilogue
-        const int r = tid;                          // row inside the tile == TMEM lane
+        // =========================================================== softmax / correction / epilogue, one warpgroup per query tile
+        const int x = warp >> 2;                         // 0: tile A, 1: tile B
+        const int r = tid & 127;                         // row inside the tile == TMEM lane
+        const int i0 = x == 0 ? iA : iB;
+        const int i1 = min(i0 + kBM, L);
         const int i = i0 + r;
-        // allowed kv range [lo, hi) of this row (closed-form omni mask); rows beyond L are harmless
-        int lo, hi;
-        if (i >= S) { lo = P; hi = L; }
-        else if (i >= P) { lo = P; hi = i + 1; }
-        else { lo = 0; hi = i + 1; }
-        hi = min(hi, L);
-        // tile-uniform bounds for the "no masking needed" fast path
-        const int max_lo = (i1 > P) ? P : 0;
-        const int min_hi = (i0 < S) ? (i0 + 1) : L;
-        const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
-        const float c = p.scale_log2;
-        float m_run = -INFINITY, l_run = 0.0f;
-        uint32_t pk[64];
+        const int t0 = x == 0 ? tA0 : tB0, t1 = x == 0 ? tA1 : tB1;
+        const bool active = x == 0 || hasB;
+        if (active) {
+            int lo, hi;                                  // allowed kv range [lo, hi) of this row
+            if (i >= S) { lo = P; hi = L; }
+            else if (i >= P) { lo = P; hi = i + 1; }
+            else { lo = 0; hi = i + 1; }
+            hi = min(hi, L);
+            const int max_lo = (i1 > P) ? P : 0;
+            const int min_hi = (i0 < S) ? (i0 + 1) : L;
+            const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+            const uint32_t s_addr = tmem + lane_base + (uint32_t)x * 128u;      // S_x, and P_x in its first 64 columns
+            const uint32_t o_addr = tmem + lane_base + 256u + (uint32_t)x * 128u;
+            const float c = p.scale_log2;
+            float m_ref = -INFINITY;                     // the (possibly stale) max the exponentials are taken against
+            float l_run = 0.0f;
+            const bool dump = p.dbg && x == 0 && qp == 0 && h == 0 && b == 0;
 
-        for (int j = 0; j < n_tiles; ++j) {
-            const int sb = j & 1;
-            const int j0 = (t0 + j) * kBN;
-            const bool full_tile = (j0 >= max_lo) && (j0 + kBN <= min_hi);
-            const int clo = lo - j0, chi = hi - j0;           // valid columns [clo, chi)
-            bar_wait(&bars->s_full[sb], (uint32_t)(j >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t s_addr = tmem + lane_base + (uint32_t)sb * 128u;
-            // pass 1: row max
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(s_addr + ch * 32, v);
-                if (p.dbg && blockIdx.x == gridDim.x - 1 && h == 0 && b == 0 && j == 0)
-                    for (int q = 0; q < 32; ++q) p.dbg[r * 128 + ch * 32 + q] = __uint_as_float(v[q]);
-                if (full_tile) {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(v[q]));
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const int col = ch * 32 + q;
-                        mx = fmaxf(mx, (col >= clo && col < chi) ? __uint_as_float(v[q]) : -INFINITY);
-                    }
-                }
-            }
-            const float m_new = fmaxf(m_run, mx * c);
-            const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
-            const float alpha = ex2(m_run - m_use);           // 0 when m_run == -inf
-            // pass 2: probabilities, row sum, bf16 pack
-            float rs = 0.0f;
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(s_addr + ch * 32, v);
-#pragma unroll
-                for (int q = 0; q < 32; q += 2) {
-                    const int col = ch * 32 + q;
-                    float e0 = ex2(fmaf(__uint_as_float(v[q]), c, -m_use));
-                    float e1 = ex2(fmaf(__uint_as_float(v[q + 1]), c, -m_use));
-                    if (!full_tile) {
-                        e0 = (col >= clo && col < chi) ? e0 : 0.0f;
-                        e1 = (col + 1 >= clo && col + 1 < chi) ? e1 : 0.0f;
-                    }
-                    const uint32_t w = pack_bf16(e0, e1);
-                    pk[(ch * 32 + q) >> 1] = w;
-                    // the row sum uses the bf16-rounded values the tensor core will see
-                    rs += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
-                }
-            }
-            tc_fence_before();
-            bar_arrive(&bars->s_empty[sb]);
-            // O must be complete (PV_{j-1}) before it is rescaled and before P is overwritten
-            if (j > 0) {
-                bar_wait(&bars->pv_done, (uint32_t)(j - 1) & 1u);
+            for (int t = t0; t < t1; ++t) {
+                const int n = t - t0;
+                const int j0 = t * kBN;
+                const bool full_tile = (j0 >= max_lo) && (j0 + kBN <= min_hi);
+                const int clo = lo - j0, chi = hi - j0;
+                bar_wait(&bars->s_full[x], (uint32_t)n & 1u);
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+                // pass 1: row max of the scores
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(s_addr + ch * 32, v);
+                    if (dump && n == 0)
+                        for (int q = 0; q < 32; ++q) p.dbg[r * 128 + ch * 32 + q] = __uint_as_float(v[q]);
+                    if (full_tile) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(v[q]));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const int col = ch * 32 + q;
+                            mx = fmaxf(mx, (col >= clo && col < chi) ? __uint_as_float(v[q]) : -INFINITY);
+                        }
+                    }
+                }
+                // lazy rescaling: keep m_ref while the true max stays within 2^tau of it (exact: O, l and P share m_ref)
+                const float m_true = fmaxf(m_ref, mx * c);
+                const bool move = (m_true - m_ref > kRescaleTau) || (m_ref == -INFINITY && m_true != -INFINITY);
+                const float m_new = move ? m_true : m_ref;
+                const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
+                const float alpha = move ? ex2(m_ref - m_use) : 1.0f;          // 0 when m_ref was -inf
+                // S_x(t) complete implies P_x V_(t-1) complete (same issuing thread, in order): O_x can be rescaled now
+                if (n > 0 && __any_sync(0xffffffffu, move)) {
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ++ch) {
                         uint32_t v[32];
-                        tmem_ld32(tmem + lane_base + 256u + ch * 32, v);
+                        tmem_ld32(o_addr + ch * 32, v);
 #pragma unroll
                         for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) * alpha);
-                        tmem_st32(tmem + lane_base + 256u + ch * 32, v);
+                        tmem_st32(o_addr + ch * 32, v);
                     }
-                    tmem_st_wait();
                 }
-            }
-            l_run = l_run * alpha + rs;
-            m_run = m_new;
-            // P -> shared memory, K-major SWIZZLE_128B: 16-byte chunk index XOR (row & 7)
-            {
-                uint8_t* prow = smem + kOffP + (uint32_t)r * 128u;
-#pragma unroll
-                for (int cc = 0; cc < 16; ++cc) {             // 16 chunks of 8 columns
-                    const uint32_t panel = (uint32_t)(cc >> 3) * kPanelBytes;
-                    const uint32_t chunk = (uint32_t)((cc & 7) ^ (r & 7)) << 4;
-                    *reinterpret_cast<uint4*>(prow + panel + chunk) = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-                }
-            }
-            if (p.dbg && blockIdx.x == gridDim.x - 1 && h == 0 && b == 0 && j == 0)
-                for (int q = 0; q < 64; ++q) {
-                    p.dbg[16384 + r * 128 + 2 * q] = __uint_as_float(pk[q] << 16);
-                    p.dbg[16384 + r * 128 + 2 * q + 1] = __uint_as_float(pk[q] & 0xffff0000u);
-                }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tc_fence_before();
-            bar_arrive(&bars->p_full);
-        }
-        // epilogue: O / l -> bf16 -> global
-        bar_wait(&bars->pv_done, (uint32_t)(n_tiles - 1) & 1u);
-        tc_fence_after();
-        const float inv_l = 1.0f / l_run;
-        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.a.out) + (int64_t)b * p.a.o_sb + (int64_t)i * p.a.o_sl + (int64_t)h * p.a.o_sh;
+                // pass 2: probabilities -> bf16 pairs -> P_x in tensor memory (A operand of the second GEMM)
+                float rs = 0.0f;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-            uint32_t v[32];
-            tmem_ld32(tmem + lane_base + 256u + ch * 32, v);
-            if (i < L) {
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t v[32], pk[16];
+                    tmem_ld32(s_addr + ch * 32, v);
 #pragma unroll
-                for (int q = 0; q < 32; q += 8) {
-                    uint4 o;
-                    o.x = pack_bf16(__uint_as_float(v[q]) * inv_l, __uint_as_float(v[q + 1]) * inv_l);
-                    o.y = pack_bf16(__uint_as_float(v[q + 2]) * inv_l, __uint_as_float(v[q + 3]) * inv_l);
-                    o.z = pack_bf16(__uint_as_float(v[q + 4]) * inv_l, __uint_as_float(v[q + 5]) * inv_l);
-                    o.w = pack_bf16(__uint_as_float(v[q + 6]) * inv_l, __uint_as_float(v[q + 7]) * inv_l);
-                    *reinterpret_cast<uint4*>(orow + ch * 32 + q) = o;
+                    for (int q = 0; q < 32; q += 2) {
+                        const int col = ch * 32 + q;
+                        float e0 = ex2(fmaf(__uint_as_float(v[q]), c, -m_use));
+                        float e1 = ex2(fmaf(__uint_as_float(v[q + 1]), c, -m_use));
+                        if (!full_tile) {
+                            e0 = (col >= clo && col < chi) ? e0 : 0.0f;
+                            e1 = (col + 1 >= clo && col + 1 < chi) ? e1 : 0.0f;
+                        }
+                        const uint32_t w = pack_bf16(e0, e1);
+                        pk[q >> 1] = w;
+                        rs += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);   // what the tensor core will see
+                    }
+                    if (dump && n == 0)
+                        for (int q = 0; q < 16; ++q) {
+                            p.dbg[16384 + r * 128 + ch * 32 + 2 * q] = __uint_as_float(pk[q] << 16);
+                            p.dbg[16384 + r * 128 + ch * 32 + 2 * q + 1] = __uint_as_float(pk[q] & 0xffff0000u);
+                        }
+                    tmem_st16(s_addr + ch * 16, pk);
+                }
+                tmem_st_wait();
+                l_run = l_run * alpha + rs;
+                m_ref = m_new;
+                tc_fence_before();
+                bar_arrive(&bars->p_full[x]);
+            }
+            // epilogue: O / l -> bf16 -> global
+            bar_wait(&bars->o_done[x], 0);
+            tc_fence_after();
+            const float inv_l = 1.0f / l_run;
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.a.out) + (int64_t)b * p.a.o_sb + (int64_t)i * p.a.o_sl + (int64_t)h * p.a.o_sh;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(o_addr + ch * 32, v);
+                if (i < L) {
+#pragma unroll
+                    for (int q = 0; q < 32; q += 8) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(v[q]) * inv_l, __uint_as_float(v[q + 1]) * inv_l);
+                        o.y = pack_bf16(__uint_as_float(v[q + 2]) * inv_l, __uint_as_float(v[q + 3]) * inv_l);
+                        o.z = pack_bf16(__uint_as_float(v[q + 4]) * inv_l, __uint_as_float(v[q + 5]) * inv_l);
+                        o.w = pack_bf16(__uint_as_float(v[q + 6]) * inv_l, __uint_as_float(v[q + 7]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + ch * 32 + q) = o;
+                    }
                 }
             }
+            tc_fence_before();
         }
-        tc_fence_before();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
@@ -470,16 +527,16 @@ int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, c
     AttnParams p;
     p.a = a;
     p.scale_log2 = a.scale * 1.4426950408889634f;
-    p.n_qtiles = (a.L + kBM - 1) / kBM;
+    p.n_qpairs = (a.L + 2 * kBM - 1) / (2 * kBM);
     p.dbg = g_attn_dbg;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(omni_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem);
+        cudaError_t e = cudaFuncSetAttribute(omni_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttn2Smem);
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    dim3 grid((unsigned)p.n_qtiles, (unsigned)a.Hq, (unsigned)a.B);
-    omni_attention_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, p);
+    dim3 grid((unsigned)p.n_qpairs, (unsigned)a.Hq, (unsigned)a.B);
+    omni_attention_kernel<<<grid, kAttn2Threads, kAttn2Smem, stream>>>(tq, tk, tv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;

@@ -1,0 +1,64 @@
+"""Omni-attention sweep (BASELINE.json config 4): S in {128,256,512} text rows, N in {256,1024} image tokens,
+B=16, 12Q/2KV heads, D=128; times 28 launches back to back with CUDA events; prints algorithmic TFLOP/s and
+the torch SDPA (dense mask, what the reference runs) time beside it."""
+import json, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ml_unigen_b200 import ops
+from oracle import backbone_oracle as BO
+
+def flops(P, S, L, N, Hq=12, D=128):
+    return 4 * D * Hq * sum(p * (p + 1) // 2 + (s - p) * (s - p + 1) // 2 + (N + 2) * (L - p) for p, s in zip(P, S))
+
+def main():
+    dev = torch.device("cuda:0")
+    B, Hq, Hkv, D = 16, 12, 2, 128
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    pk = peaks.get("bf16_tflops_sustained", 1400.0)
+    out = []
+    cfgs = [(137, 1024, 0), (137, 1024, 57), (137, 256, 0), (256, 1024, 128), (512, 1024, 0), (512, 256, 256), (128, 256, 64)]
+    if os.environ.get("QUICK"):
+        cfgs = cfgs[:2]
+    for S, N, Pp in cfgs:
+        L = S + N + 2
+        g = torch.Generator(device=dev).manual_seed(0)
+        q = torch.randn(B, L, Hq, D, device=dev, generator=g).bfloat16()
+        k = torch.randn(B, L, Hkv, D, device=dev, generator=g).bfloat16()
+        v = torch.randn(B, L, Hkv, D, device=dev, generator=g).bfloat16()
+        P = torch.full((B,), Pp, dtype=torch.int32, device=dev)
+        St = torch.full((B,), S, dtype=torch.int32, device=dev)
+        o = torch.empty_like(q)
+        for _ in range(5):
+            ops.omni_attention(q, k, v, P, St, D ** -0.5, out=o)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(28):
+            ops.omni_attention(q, k, v, P, St, D ** -0.5, out=o)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3 / 28
+        fl = flops([Pp] * B, [S] * B, L, N)
+        row = dict(S=S, N=N, P=Pp, L=L, ms=round(t * 1e3, 4), alg_TFLOPs=round(fl / t / 1e12, 1), dense_TFLOPs=round(4 * B * Hq * L * L * D / t / 1e12, 1),
+                   frac_sustained=round(fl / t / 1e12 / pk, 3))
+        if not os.environ.get("NO_SDPA"):
+            mask = BO.omni_additive_mask(P, St, L, torch.bfloat16)
+            qq, kk, vv = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3).repeat_interleave(6, 1), v.permute(0, 2, 1, 3).repeat_interleave(6, 1)
+            for _ in range(2):
+                torch.nn.functional.scaled_dot_product_attention(qq, kk, vv, attn_mask=mask, scale=D ** -0.5)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                kk2 = k.permute(0, 2, 1, 3).repeat_interleave(6, 1); vv2 = v.permute(0, 2, 1, 3).repeat_interleave(6, 1)
+                torch.nn.functional.scaled_dot_product_attention(qq, kk2, vv2, attn_mask=mask, scale=D ** -0.5)
+            e1.record()
+            torch.cuda.synchronize()
+            row["torch_sdpa_dense_mask_ms"] = round(e0.elapsed_time(e1) / 5, 4)
+        print(json.dumps(row), flush=True)
+        out.append(row)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "attention_sweep.json"), "w"), indent=1)
+
+if __name__ == "__main__":
+    main()
