@@ -138,8 +138,9 @@ int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, int64_t M, in
 int ug_swiglu(const void* gate_up_bf16, void* act_bf16, int64_t M, int I, void* stream);
 int ug_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64_t M, int H, int64_t vocab, void* stream);
 
-/* test hook: float[2*128*128] receiving the raw scores S and the bf16 probabilities P of the first kv tile
- * of the first query tile of (b=0, h=0) of subsequent ug_omni_attention_bf16 calls of this thread; NULL = off */
+/* test hook: float[2*128*128 + 2048] receiving the raw scores S and the bf16 probabilities P of the first kv tile
+ * of the first query tile of (b=0, h=0), followed by 2048 cycle stamps of CTA (0,0,0) (tools/attn_timeline.py), of
+ * subsequent ug_omni_attention_bf16 calls of this thread; NULL = off */
 void ug_debug_set_attn_dump(float* dump);
 
 #ifdef __cplusplus

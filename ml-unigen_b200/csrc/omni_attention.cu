@@ -178,6 +178,55 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         : "memory");
 }
 
+
+// ---- softmax inner loops, specialised on "tile needs masking" so the hot path has no per-element branches ----
+template <bool kMasked>
+__device__ __forceinline__ float row_max_chunk(const uint32_t (&v)[32], int cbase, int clo, int chi, float mx)
+{
+    float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 32; q += 4) {
+        float a = __uint_as_float(v[q]), b = __uint_as_float(v[q + 1]), c = __uint_as_float(v[q + 2]), d = __uint_as_float(v[q + 3]);
+        if (kMasked) {
+            const int col = cbase + q;
+            a = (col >= clo && col < chi) ? a : -INFINITY;
+            b = (col + 1 >= clo && col + 1 < chi) ? b : -INFINITY;
+            c = (col + 2 >= clo && col + 2 < chi) ? c : -INFINITY;
+            d = (col + 3 >= clo && col + 3 < chi) ? d : -INFINITY;
+        }
+        m0 = fmaxf(m0, a); m1 = fmaxf(m1, b); m2 = fmaxf(m2, c); m3 = fmaxf(m3, d);
+    }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// p = 2^(s*c - m) for 32 scores -> 16 packed bf16 pairs; returns the fp32 sum of the 32 probabilities
+template <bool kMasked>
+__device__ __forceinline__ float prob_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float m_use, int cbase,
+                                            int clo, int chi)
+{
+    const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_use, -m_use);
+    float2 acc0 = make_float2(0.0f, 0.0f), acc1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int q = 0; q < 32; q += 4) {
+        float2 x0 = __ffma2_rn(make_float2(__uint_as_float(v[q]), __uint_as_float(v[q + 1])), c2, nm2);
+        float2 x1 = __ffma2_rn(make_float2(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3])), c2, nm2);
+        float2 e0 = make_float2(ex2(x0.x), ex2(x0.y));
+        float2 e1 = make_float2(ex2(x1.x), ex2(x1.y));
+        if (kMasked) {
+            const int col = cbase + q;
+            e0.x = (col >= clo && col < chi) ? e0.x : 0.0f;
+            e0.y = (col + 1 >= clo && col + 1 < chi) ? e0.y : 0.0f;
+            e1.x = (col + 2 >= clo && col + 2 < chi) ? e1.x : 0.0f;
+            e1.y = (col + 3 >= clo && col + 3 < chi) ? e1.y : 0.0f;
+        }
+        pk[q >> 1] = pack_bf16(e0.x, e0.y);
+        pk[(q >> 1) + 1] = pack_bf16(e1.x, e1.y);
+        acc0 = __fadd2_rn(acc0, e0);
+        acc1 = __fadd2_rn(acc1, e1);
+    }
+    return (acc0.x + acc0.y) + (acc1.x + acc1.y);
+}
+
 // kv tile range [t0, t1) needed by the query rows [i0, i1) under the omni mask (P = pad_len, S = soi_idx)
 __device__ __forceinline__ void kv_range(int i0, int i1, int P, int S, int L, int& t0, int& t1)
 {
@@ -253,6 +302,13 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
+    // test hook: cycle stamps of the heaviest CTA (blockIdx 0,0,0) at dbg[32768 + role*512 + iter*8 + event]
+    const bool tl = p.dbg && blockIdx.x == 0 && h == 0 && b == 0;
+    const uint32_t clk0 = (uint32_t)clock();
+#define UG_TL(role, iter, ev)                                                                            \
+    do {                                                                                                 \
+        if (tl && (iter) < 64) p.dbg[32768 + (role) * 512 + (iter) * 8 + (ev)] = (float)((uint32_t)clock() - clk0); \
+    } while (0)
 
     if (warp == 8) {
         // =========================================================== TMA producer
@@ -322,7 +378,9 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 for (int x = 0; x < 2; ++x) {
                     if (in_range(x, t)) {
                         // O_x (+)= P_x V_t  once the softmax warpgroup x has written P_x
+                        UG_TL(2, 2 * j + x, 0);
                         bar_wait(&bars->p_full[x], (uint32_t)np[x] & 1u);
+                        UG_TL(2, 2 * j + x, 1);
                         if (!v_ready) { bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u); v_ready = true; }
                         tc_fence_after();
                         const uint32_t v_addr = s_u32(smem + kOff2V + s * kTileBytes);
@@ -332,6 +390,7 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                             tc_mma_ts(tmem + 256u + (uint32_t)x * 128u, tmem + (uint32_t)x * 128u + (uint32_t)k * 8u,
                                       desc_mnmajor(v_addr + (uint32_t)k * 16u * 128u), idesc_pv, (t > first_t || k > 0) ? 1u : 0u);
                         ++np[x];
+                        UG_TL(2, 2 * j + x, 2);
                         const int last_t = (x == 0 ? tA1 : tB1) - 1;
                         if (t == last_t) tc_commit(&bars->o_done[x]);
                     }
@@ -340,6 +399,7 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     if (next) {
                         if (x == 0) sn = qk_pair(t + 1);
                         if (in_range(x, t + 1)) issue_qk(x, t + 1);
+                        UG_TL(2, 2 * j + x, 3);
                     }
                 }
                 if (!v_ready) { bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u); }
@@ -377,8 +437,10 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 const int j0 = t * kBN;
                 const bool full_tile = (j0 >= max_lo) && (j0 + kBN <= min_hi);
                 const int clo = lo - j0, chi = hi - j0;
+                if (r == 0) UG_TL(x, n, 0);
                 bar_wait(&bars->s_full[x], (uint32_t)n & 1u);
                 tc_fence_after();
+                if (r == 0) UG_TL(x, n, 1);
                 // pass 1: row max of the scores
                 float mx = -INFINITY;
 #pragma unroll 1
@@ -387,17 +449,9 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     tmem_ld32(s_addr + ch * 32, v);
                     if (dump && n == 0)
                         for (int q = 0; q < 32; ++q) p.dbg[r * 128 + ch * 32 + q] = __uint_as_float(v[q]);
-                    if (full_tile) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(v[q]));
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const int col = ch * 32 + q;
-                            mx = fmaxf(mx, (col >= clo && col < chi) ? __uint_as_float(v[q]) : -INFINITY);
-                        }
-                    }
+                    mx = full_tile ? row_max_chunk<false>(v, ch * 32, clo, chi, mx) : row_max_chunk<true>(v, ch * 32, clo, chi, mx);
                 }
+                if (r == 0) UG_TL(x, n, 2);
                 // lazy rescaling: keep m_ref while the true max stays within 2^tau of it (exact: O, l and P share m_ref)
                 const float m_true = fmaxf(m_ref, mx * c);
                 const bool move = (m_true - m_ref > kRescaleTau) || (m_ref == -INFINITY && m_true != -INFINITY);
@@ -415,25 +469,15 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                         tmem_st32(o_addr + ch * 32, v);
                     }
                 }
+                if (r == 0) UG_TL(x, n, 3);
                 // pass 2: probabilities -> bf16 pairs -> P_x in tensor memory (A operand of the second GEMM)
                 float rs = 0.0f;
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     uint32_t v[32], pk[16];
                     tmem_ld32(s_addr + ch * 32, v);
-#pragma unroll
-                    for (int q = 0; q < 32; q += 2) {
-                        const int col = ch * 32 + q;
-                        float e0 = ex2(fmaf(__uint_as_float(v[q]), c, -m_use));
-                        float e1 = ex2(fmaf(__uint_as_float(v[q + 1]), c, -m_use));
-                        if (!full_tile) {
-                            e0 = (col >= clo && col < chi) ? e0 : 0.0f;
-                            e1 = (col + 1 >= clo && col + 1 < chi) ? e1 : 0.0f;
-                        }
-                        const uint32_t w = pack_bf16(e0, e1);
-                        pk[q >> 1] = w;
-                        rs += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);   // what the tensor core will see
-                    }
+                    rs += full_tile ? prob_chunk<false>(v, pk, c, m_use, ch * 32, clo, chi)
+                                    : prob_chunk<true>(v, pk, c, m_use, ch * 32, clo, chi);
                     if (dump && n == 0)
                         for (int q = 0; q < 16; ++q) {
                             p.dbg[16384 + r * 128 + ch * 32 + 2 * q] = __uint_as_float(pk[q] << 16);
@@ -442,10 +486,12 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     tmem_st16(s_addr + ch * 16, pk);
                 }
                 tmem_st_wait();
+                if (r == 0) UG_TL(x, n, 4);
                 l_run = l_run * alpha + rs;
                 m_ref = m_new;
                 tc_fence_before();
                 bar_arrive(&bars->p_full[x]);
+                if (r == 0) UG_TL(x, n, 5);
             }
             // epilogue: O / l -> bf16 -> global
             bar_wait(&bars->o_done[x], 0);

@@ -16,7 +16,7 @@ struct AttnArgs {
     int64_t o_sb, o_sl, o_sh;
 };
 
-// test hook: float[2*128*128] receiving S (raw q.k) and P (bf16-rounded probabilities) of kv tile 0 of the
+// test hook: float[2*128*128 + 2048] receiving S (raw q.k) and P (bf16-rounded probabilities) of kv tile 0 of the
 // FIRST q tile (rows 0..127) of (b=0, h=0); nullptr = off
 void set_attn_debug(float* p);
 

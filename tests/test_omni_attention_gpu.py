@@ -54,7 +54,7 @@ def _diagnose(q, k, dump, P, S, scale):
     print("score tile max-abs err:", (s_got - s_ref).abs().max().item(), "ref max", s_ref.abs().max().item())
     print("score tile got[0,:8]", s_got[0, :8].tolist(), "ref[0,:8]", s_ref[0, :8].tolist())
     print("score tile got[1,:4]", s_got[1, :4].tolist(), "ref[1,:4]", s_ref[1, :4].tolist())
-    p_got = dump[128 * 128:].view(128, 128)[:rows, :cols]
+    p_got = dump[128 * 128:2 * 128 * 128].view(128, 128)[:rows, :cols]
     print("prob tile got[0,:8]", p_got[0, :8].tolist(), "row sums", p_got.sum(-1)[:4].tolist())
 
 
@@ -71,7 +71,7 @@ def test_omni_attention_matches_fp32_reference(dev, B, L, P, S):
     q, k, v = _mk(B, L, Hq, Hkv, D, seed=L + B, dev=dev)
     Pt = torch.tensor(P, dtype=torch.int32, device=dev)
     St = torch.tensor(S, dtype=torch.int32, device=dev)
-    dump = torch.zeros(2 * 128 * 128, dtype=torch.float32, device=dev)
+    dump = torch.zeros(2 * 128 * 128 + 2048, dtype=torch.float32, device=dev)
     _lib.lib().ug_debug_set_attn_dump(dump.data_ptr())
     try:
         out = ops.omni_attention(q, k, v, Pt, St, D ** -0.5)

@@ -1,0 +1,30 @@
+"""Cycle-stamp timeline of one omni-attention CTA (debug hook): where a kv-tile iteration spends its time."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ml_unigen_b200 import ops, _lib
+dev = torch.device("cuda:0")
+B, L, Hq, Hkv, D = 16, 1163, 12, 2, 128
+g = torch.Generator(device=dev).manual_seed(0)
+q = torch.randn(B, L, Hq, D, device=dev, generator=g).bfloat16()
+k = torch.randn(B, L, Hkv, D, device=dev, generator=g).bfloat16()
+v = torch.randn(B, L, Hkv, D, device=dev, generator=g).bfloat16()
+P = torch.zeros(B, dtype=torch.int32, device=dev)
+S = torch.full((B,), 137, dtype=torch.int32, device=dev)
+for _ in range(3):
+    ops.omni_attention(q, k, v, P, S, D ** -0.5)
+dump = torch.zeros(32768 + 2048, dtype=torch.float32, device=dev)
+_lib.lib().ug_debug_set_attn_dump(dump.data_ptr())
+ops.omni_attention(q, k, v, P, S, D ** -0.5)
+torch.cuda.synchronize()
+_lib.lib().ug_debug_set_attn_dump(None)
+t = dump[32768:].cpu().view(4, 64, 8)
+names = {0: "softmaxA", 1: "softmaxB", 2: "mma"}
+for role in (0, 1):
+    print(names[role], "events: wait_start, s_full, pass1_done, rescale_done, pass2_done, arrived")
+    for it in range(12):
+        print(it, [int(x) for x in t[role, it, :6].tolist()])
+print("mma events per (kv tile, x): wait_start, p_full, pv_issued, qk_issued")
+for it in range(24):
+    print(it // 2, "AB"[it % 2], [int(x) for x in t[2, it, :4].tolist()])
