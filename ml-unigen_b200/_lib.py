@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libunigen_b200.so")
+LIB_PATH = os.environ.get("UNIGEN_B200_LIB") or os.path.join(_HERE, "csrc", "libunigen_b200.so")   # env override: kernel experiments only
 
 UG_ABI_VERSION = 1
 SYMBOLS = (

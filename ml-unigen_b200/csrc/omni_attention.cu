@@ -75,6 +75,10 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// named barriers 2/3: the two softmax warpgroups take turns in the MUFU/FMA-heavy section, so that one tile's
+// softmax overlaps the OTHER tile's GEMMs instead of the other tile's softmax (ping-pong scheduling)
+__device__ __forceinline__ void turn_wait(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void turn_pass(int id) { asm volatile("bar.arrive %0, 256;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar)
@@ -102,6 +106,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// the same load without the wait: several can be in flight; tmem_ld_wait() + pin32() before the registers are used
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// zero-instruction barrier: makes every later use of v[] depend on this point (i.e. on the wait above)
+__device__ __forceinline__ void pin32(uint32_t (&v)[32])
+{
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
 {
@@ -179,6 +204,26 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 
 
+// 2^x for two values on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. error 7.5e-5 -- far
+// below the bf16 rounding of P): relieves the MUFU pipe, which is as loaded as the tensor core at head_dim 128.
+__device__ __forceinline__ float2 ex2_poly2(float2 x)
+{
+    const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+    x.x = fmaxf(x.x, -120.0f);
+    x.y = fmaxf(x.y, -120.0f);
+    const float2 t = __fadd2_rn(x, magic);
+    const float2 n = __fadd2_rn(t, nmagic);
+    const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+    float2 p = make_float2(0x1.c3f76p-5f, 0x1.c3f76p-5f);
+    p = __ffma2_rn(p, f, make_float2(0x1.f0de1ap-3f, 0x1.f0de1ap-3f));
+    p = __ffma2_rn(p, f, make_float2(0x1.62f31ap-1f, 0x1.62f31ap-1f));
+    p = __ffma2_rn(p, f, make_float2(0x1.fff692p-1f, 0x1.fff692p-1f));
+    float2 r;
+    r.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+    r.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+    return r;
+}
+
 // ---- softmax inner loops, specialised on "tile needs masking" so the hot path has no per-element branches ----
 template <bool kMasked>
 __device__ __forceinline__ float row_max_chunk(const uint32_t (&v)[32], int cbase, int clo, int chi, float mx)
@@ -210,8 +255,12 @@ __device__ __forceinline__ float prob_chunk(const uint32_t (&v)[32], uint32_t (&
     for (int q = 0; q < 32; q += 4) {
         float2 x0 = __ffma2_rn(make_float2(__uint_as_float(v[q]), __uint_as_float(v[q + 1])), c2, nm2);
         float2 x1 = __ffma2_rn(make_float2(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3])), c2, nm2);
-        float2 e0 = make_float2(ex2(x0.x), ex2(x0.y));
+        float2 e0 = make_float2(ex2(x0.x), ex2(x0.y));         // MUFU
+#if UG_ATTN_POLY
+        float2 e1 = ex2_poly2(x1);                              // FMA pipe
+#else
         float2 e1 = make_float2(ex2(x1.x), ex2(x1.y));
+#endif
         if (kMasked) {
             const int col = cbase + q;
             e0.x = (col >= clo && col < chi) ? e0.x : 0.0f;
@@ -244,6 +293,12 @@ constexpr uint32_t kOff2V = kOff2K + kKVStages * kTileBytes;
 constexpr uint32_t kOff2Bar = kOff2V + kKVStages * kTileBytes;
 constexpr uint32_t kAttn2Smem = kOff2Bar + 256 + 1024;
 constexpr int kAttn2Threads = 320;           // 2 softmax warpgroups (one per query tile) + TMA warp + MMA warp
+#ifndef UG_ATTN_POLY
+#define UG_ATTN_POLY 0       // 1: every second pair of exponentials on the FMA pipe (polynomial), 0: all on MUFU
+#endif
+#ifndef UG_ATTN_TURNS
+#define UG_ATTN_TURNS 0      // 1: the two softmax warpgroups alternate (named barriers), 0: free running
+#endif
 constexpr float kRescaleTau = 8.0f;          // keep a stale row max until the true max moved by > 2^8 (exact, lazy rescaling)
 
 struct Attn2Bars {
@@ -432,7 +487,14 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             float l_run = 0.0f;
             const bool dump = p.dbg && x == 0 && qp == 0 && h == 0 && b == 0;
 
-            for (int t = t0; t < t1; ++t) {
+            const bool turns = hasB && (UG_ATTN_TURNS != 0);   // both warpgroups alive: alternate, tile A first
+            if (turns && x == 1) turn_pass(2);
+            for (int t = tU0; t < tU1; ++t) {
+                const bool mine = t >= t0 && t < t1;
+                if (!mine) {                             // keep the alternation going while the other tile still has work
+                    if (turns) { turn_wait(2 + x); turn_pass(3 - x); }
+                    continue;
+                }
                 const int n = t - t0;
                 const int j0 = t * kBN;
                 const bool full_tile = (j0 >= max_lo) && (j0 + kBN <= min_hi);
@@ -440,16 +502,34 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 if (r == 0) UG_TL(x, n, 0);
                 bar_wait(&bars->s_full[x], (uint32_t)n & 1u);
                 tc_fence_after();
+                if (turns) turn_wait(2 + x);
                 if (r == 0) UG_TL(x, n, 1);
-                // pass 1: row max of the scores
+                // the whole score row (128 fp32) comes to registers in one go: four loads in flight, one wait
+                uint32_t v0[32], v1[32], v2[32], v3[32];
+                tmem_ld32_async(s_addr, v0);
+                tmem_ld32_async(s_addr + 32, v1);
+                tmem_ld32_async(s_addr + 64, v2);
+                tmem_ld32_async(s_addr + 96, v3);
+                tmem_ld_wait();
+                pin32(v0); pin32(v1); pin32(v2); pin32(v3);
+                if (dump && n == 0)
+                    for (int q = 0; q < 32; ++q) {
+                        p.dbg[r * 128 + q] = __uint_as_float(v0[q]);
+                        p.dbg[r * 128 + 32 + q] = __uint_as_float(v1[q]);
+                        p.dbg[r * 128 + 64 + q] = __uint_as_float(v2[q]);
+                        p.dbg[r * 128 + 96 + q] = __uint_as_float(v3[q]);
+                    }
                 float mx = -INFINITY;
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(s_addr + ch * 32, v);
-                    if (dump && n == 0)
-                        for (int q = 0; q < 32; ++q) p.dbg[r * 128 + ch * 32 + q] = __uint_as_float(v[q]);
-                    mx = full_tile ? row_max_chunk<false>(v, ch * 32, clo, chi, mx) : row_max_chunk<true>(v, ch * 32, clo, chi, mx);
+                if (full_tile) {
+                    mx = row_max_chunk<false>(v0, 0, clo, chi, mx);
+                    mx = row_max_chunk<false>(v1, 32, clo, chi, mx);
+                    mx = row_max_chunk<false>(v2, 64, clo, chi, mx);
+                    mx = row_max_chunk<false>(v3, 96, clo, chi, mx);
+                } else {
+                    mx = row_max_chunk<true>(v0, 0, clo, chi, mx);
+                    mx = row_max_chunk<true>(v1, 32, clo, chi, mx);
+                    mx = row_max_chunk<true>(v2, 64, clo, chi, mx);
+                    mx = row_max_chunk<true>(v3, 96, clo, chi, mx);
                 }
                 if (r == 0) UG_TL(x, n, 2);
                 // lazy rescaling: keep m_ref while the true max stays within 2^tau of it (exact: O, l and P share m_ref)
@@ -470,21 +550,26 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     }
                 }
                 if (r == 0) UG_TL(x, n, 3);
-                // pass 2: probabilities -> bf16 pairs -> P_x in tensor memory (A operand of the second GEMM)
+                // probabilities -> bf16 pairs -> P_x in tensor memory (A operand of the second GEMM)
                 float rs = 0.0f;
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t v[32], pk[16];
-                    tmem_ld32(s_addr + ch * 32, v);
-                    rs += full_tile ? prob_chunk<false>(v, pk, c, m_use, ch * 32, clo, chi)
-                                    : prob_chunk<true>(v, pk, c, m_use, ch * 32, clo, chi);
-                    if (dump && n == 0)
-                        for (int q = 0; q < 16; ++q) {
-                            p.dbg[16384 + r * 128 + ch * 32 + 2 * q] = __uint_as_float(pk[q] << 16);
-                            p.dbg[16384 + r * 128 + ch * 32 + 2 * q + 1] = __uint_as_float(pk[q] & 0xffff0000u);
-                        }
-                    tmem_st16(s_addr + ch * 16, pk);
+                {
+                    uint32_t pk[16];
+#define UG_PROB_CHUNK(vv, ch)                                                                                     \
+    rs += full_tile ? prob_chunk<false>(vv, pk, c, m_use, (ch) * 32, clo, chi)                                    \
+                    : prob_chunk<true>(vv, pk, c, m_use, (ch) * 32, clo, chi);                                    \
+    if (dump && n == 0)                                                                                           \
+        for (int q = 0; q < 16; ++q) {                                                                            \
+            p.dbg[16384 + r * 128 + (ch) * 32 + 2 * q] = __uint_as_float(pk[q] << 16);                            \
+            p.dbg[16384 + r * 128 + (ch) * 32 + 2 * q + 1] = __uint_as_float(pk[q] & 0xffff0000u);                \
+        }                                                                                                         \
+    tmem_st16(s_addr + (ch) * 16, pk);
+                    UG_PROB_CHUNK(v0, 0)
+                    UG_PROB_CHUNK(v1, 1)
+                    UG_PROB_CHUNK(v2, 2)
+                    UG_PROB_CHUNK(v3, 3)
+#undef UG_PROB_CHUNK
                 }
+                if (turns) turn_pass(3 - x);
                 tmem_st_wait();
                 if (r == 0) UG_TL(x, n, 4);
                 l_run = l_run * alpha + rs;
