@@ -121,6 +121,18 @@ int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* ou
                            int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
                            void* stream);
 
+/* The same for a window of query rows: q and out are [B, Lq, Hq, D] and hold the sequence rows
+ * [q_row_offset, q_row_offset + Lq); k, v still span all L rows.  With q_row_offset = soi_idx this is the
+ * per-step pass of the text-prefix K/V reuse: rows < soi_idx never see the image block,
+ * so their K/V are computed once per generation and only the N+2 image-block rows are recomputed each step. */
+int ug_omni_attention_rows_bf16(const void* q, const void* k, const void* v, void* out,
+                                const int32_t* pad_len, const int32_t* soi_idx,
+                                int B, int L, int Lq, int q_row_offset, int Hq, int Hkv, int D, float scale,
+                                int64_t q_stride_b, int64_t q_stride_l, int64_t q_stride_h,
+                                int64_t kv_stride_b, int64_t kv_stride_l, int64_t kv_stride_h,
+                                int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
+                                void* stream);
+
 /* ---- row-wise kernels of the Qwen2 decoder layer (transformers models/qwen2/modeling_qwen2.py) ------------
  * The GEMMs around them stay on cuBLAS in this round; these four replace the
  * ATen elementwise chains of Qwen2RMSNorm (+ residual add), apply_rotary_pos_emb, Qwen2MLP's

@@ -121,9 +121,11 @@ class QwenBackboneB200:
         B, L = token_ids.shape
         return ops.embed_rows(self.embed, token_ids.contiguous()).view(B, L, self.cfg.hidden_size)
 
-    def forward(self, x: torch.Tensor, pad_len: torch.Tensor, soi_idx: torch.Tensor, rows: Optional[slice] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, pad_len: torch.Tensor, soi_idx: torch.Tensor, rows: Optional[slice] = None,
+                kv_cache: Optional[list] = None) -> torch.Tensor:
         """x: fp32 [B,L,H] embeddings (consumed as the residual stream, modified in place).
-        Returns the final-norm hidden states, bf16 [B,L,H] (or [B,rows,H] when `rows` is given)."""
+        Returns the final-norm hidden states, bf16 [B,L,H] (or [B,rows,H] when `rows` is given).
+        With `kv_cache` (from `new_kv_cache`) the post-RoPE K/V of every layer are kept for `forward_suffix`."""
         cfg = self.cfg
         B, L, H = x.shape
         Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
@@ -132,28 +134,75 @@ class QwenBackboneB200:
         cos, sin = self._rope(L)
         scale = D ** -0.5
         delta = None
-        for ly in self.layers:
+        for li, ly in enumerate(self.layers):
             h = ops.add_rmsnorm(x2, ly["ln1"], cfg.rms_norm_eps, delta)
             qkv = F.linear(h, ly["wqkv"], ly["bqkv"])
             ops.rope_qk_(qkv, cos, sin, L, Hq, Hkv, D)
             q = qkv[:, : Hq * D].view(B, L, Hq, D)
-            k = qkv[:, Hq * D: (Hq + Hkv) * D].view(B, L, Hkv, D)
-            v = qkv[:, (Hq + Hkv) * D:].view(B, L, Hkv, D)
-            ev = self.attn_events
-            if ev is not None:
-                e0 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-            a = ops.omni_attention(q, k, v, pad_len, soi_idx, scale)
-            if ev is not None:
-                e1 = torch.cuda.Event(enable_timing=True)
-                e1.record()
-                ev.append((e0, e1))
+            if kv_cache is not None:
+                kv_cache[li].copy_(qkv[:, Hq * D:].view(B, L, 2, Hkv, D))
+                k, v = kv_cache[li][:, :, 0], kv_cache[li][:, :, 1]
+            else:
+                k = qkv[:, Hq * D: (Hq + Hkv) * D].view(B, L, Hkv, D)
+                v = qkv[:, (Hq + Hkv) * D:].view(B, L, Hkv, D)
+            a = self._attention(q, k, v, pad_len, soi_idx, scale, 0)
             o = F.linear(a.view(M, Hq * D), ly["wo"])
             h = ops.add_rmsnorm(x2, ly["ln2"], cfg.rms_norm_eps, o)
             act = ops.swiglu(F.linear(h, ly["wgu"]))
             delta = F.linear(act, ly["wd"])
         hn = ops.add_rmsnorm(x2, self.final_norm, cfg.rms_norm_eps, delta).view(B, L, H)
         return hn if rows is None else hn[:, rows]
+
+    def new_kv_cache(self, B: int, L: int) -> list:
+        """Per-layer post-RoPE K/V, bf16 [B, L, 2, Hkv, D] (19 MB per layer at B=16, L=1163)."""
+        cfg = self.cfg
+        return [torch.empty(B, L, 2, cfg.num_key_value_heads, cfg.head_dim, dtype=torch.bfloat16, device=self.device)
+                for _ in self.layers]
+
+    def forward_suffix(self, x: torch.Tensor, pad_len: torch.Tensor, soi_idx: torch.Tensor, s0: int, kv_cache: list,
+                       rows: Optional[slice] = None) -> torch.Tensor:
+        """Text-prefix K/V reuse.  Rows < soi_idx never attend to the image block
+        (training/prompting_utils.py:994-1011), so their hidden states and K/V are identical in every MaskGIT
+        step.  `x` holds only the rows [s0, L) (s0 = the common soi_idx): fp32 [B, Ls, H]; `kv_cache` holds the
+        K/V of all L rows from the step-0 `forward(..., kv_cache=...)`; its rows [s0, L) are refreshed here.
+        Every linear layer runs on Ls = N+2 rows instead of L."""
+        cfg = self.cfg
+        B, Ls, H = x.shape
+        L = kv_cache[0].shape[1]
+        assert s0 + Ls == L
+        Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        M = B * Ls
+        x2 = x.view(M, H)
+        cos, sin = self._rope(L)
+        cos, sin = cos[s0:], sin[s0:]                       # positions s0 .. L-1 (contiguous row slices)
+        scale = D ** -0.5
+        delta = None
+        for li, ly in enumerate(self.layers):
+            h = ops.add_rmsnorm(x2, ly["ln1"], cfg.rms_norm_eps, delta)
+            qkv = F.linear(h, ly["wqkv"], ly["bqkv"])
+            ops.rope_qk_(qkv, cos, sin, Ls, Hq, Hkv, D)
+            q = qkv[:, : Hq * D].view(B, Ls, Hq, D)
+            kv_cache[li][:, s0:].copy_(qkv[:, Hq * D:].view(B, Ls, 2, Hkv, D))
+            k, v = kv_cache[li][:, :, 0], kv_cache[li][:, :, 1]
+            a = self._attention(q, k, v, pad_len, soi_idx, scale, s0)
+            o = F.linear(a.view(M, Hq * D), ly["wo"])
+            h = ops.add_rmsnorm(x2, ly["ln2"], cfg.rms_norm_eps, o)
+            act = ops.swiglu(F.linear(h, ly["wgu"]))
+            delta = F.linear(act, ly["wd"])
+        hn = ops.add_rmsnorm(x2, self.final_norm, cfg.rms_norm_eps, delta).view(B, Ls, H)
+        return hn if rows is None else hn[:, rows]
+
+    def _attention(self, q, k, v, pad_len, soi_idx, scale, q_offset):
+        ev = self.attn_events
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        a = ops.omni_attention(q, k, v, pad_len, soi_idx, scale, q_offset=q_offset)
+        if ev is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            ev.append((e0, e1, q.shape[1]))
+        return a
 
     def codebook_logits(self, hidden_img: torch.Tensor, text_vocab_size: int, V: int) -> torch.Tensor:
         """bf16 [B,N,H] -> bf16 [B,N,V]: tied LM head restricted to rows [text_vocab, text_vocab+V)."""

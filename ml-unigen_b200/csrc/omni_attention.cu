@@ -330,12 +330,15 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     P = max(0, min(P, L));
     S = max(P, min(S, L));
 
-    // the two query tiles of this CTA and the kv tiles each of them needs
-    const int iA = qp * 2 * kBM, iB = iA + kBM;
-    const bool hasB = iB < L;
+    // the two query tiles of this CTA (local rows lA/lB of q, absolute sequence rows iA/iB) and the kv tiles they need
+    const int Lq = p.a.Lq, q0 = p.a.q0;
+    const int lA = qp * 2 * kBM, lB = lA + kBM;
+    const int iA = q0 + lA, iB = q0 + lB;
+    const int iEnd = min(q0 + Lq, L);
+    const bool hasB = lB < Lq;
     int tA0, tA1, tB0 = 0, tB1 = 0;
-    kv_range(iA, min(iA + kBM, L), P, S, L, tA0, tA1);
-    if (hasB) kv_range(iB, min(iB + kBM, L), P, S, L, tB0, tB1);
+    kv_range(iA, min(iA + kBM, iEnd), P, S, L, tA0, tA1);
+    if (hasB) kv_range(iB, min(iB + kBM, iEnd), P, S, L, tB0, tB1);
     const int tU0 = hasB ? min(tA0, tB0) : tA0;
     const int tU1 = hasB ? max(tA1, tB1) : tA1;
 
@@ -369,11 +372,11 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         // =========================================================== TMA producer
         if (lane == 0) {
             bar_expect_tx(&bars->q_full, hasB ? 2 * kTileBytes : kTileBytes);
-            tma_load_4d(smem + kOff2QA, &tm_q, &bars->q_full, 0, iA, h, b);
-            tma_load_4d(smem + kOff2QA + kPanelBytes, &tm_q, &bars->q_full, 64, iA, h, b);
+            tma_load_4d(smem + kOff2QA, &tm_q, &bars->q_full, 0, lA, h, b);
+            tma_load_4d(smem + kOff2QA + kPanelBytes, &tm_q, &bars->q_full, 64, lA, h, b);
             if (hasB) {
-                tma_load_4d(smem + kOff2QB, &tm_q, &bars->q_full, 0, iB, h, b);
-                tma_load_4d(smem + kOff2QB + kPanelBytes, &tm_q, &bars->q_full, 64, iB, h, b);
+                tma_load_4d(smem + kOff2QB, &tm_q, &bars->q_full, 0, lB, h, b);
+                tma_load_4d(smem + kOff2QB + kPanelBytes, &tm_q, &bars->q_full, 64, lB, h, b);
             }
             for (int t = tU0; t < tU1; ++t) {
                 const int j = t - tU0;
@@ -467,8 +470,9 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         const int x = warp >> 2;                         // 0: tile A, 1: tile B
         const int r = tid & 127;                         // row inside the tile == TMEM lane
         const int i0 = x == 0 ? iA : iB;
-        const int i1 = min(i0 + kBM, L);
+        const int i1 = min(i0 + kBM, iEnd);
         const int i = i0 + r;
+        const int lrow = (x == 0 ? lA : lB) + r;           // row of q / out
         const int t0 = x == 0 ? tA0 : tB0, t1 = x == 0 ? tA1 : tB1;
         const bool active = x == 0 || hasB;
         if (active) {
@@ -582,12 +586,12 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             bar_wait(&bars->o_done[x], 0);
             tc_fence_after();
             const float inv_l = 1.0f / l_run;
-            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.a.out) + (int64_t)b * p.a.o_sb + (int64_t)i * p.a.o_sl + (int64_t)h * p.a.o_sh;
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.a.out) + (int64_t)b * p.a.o_sb + (int64_t)lrow * p.a.o_sl + (int64_t)h * p.a.o_sh;
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t v[32];
                 tmem_ld32(o_addr + ch * 32, v);
-                if (i < L) {
+                if (lrow < Lq) {
 #pragma unroll
                     for (int q = 0; q < 32; q += 8) {
                         uint4 o;
@@ -649,7 +653,7 @@ int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, c
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { snprintf(msg, msg_len, "cuTensorMapEncodeTiled entry point not available"); return -6; }
     CUtensorMap tq, tk, tv;
-    if (!make_map(enc, &tq, a.q, a.L, a.Hq, a.B, a.q_sb, a.q_sl, a.q_sh) ||
+    if (!make_map(enc, &tq, a.q, a.Lq, a.Hq, a.B, a.q_sb, a.q_sl, a.q_sh) ||
         !make_map(enc, &tk, a.k, a.L, a.Hkv, a.B, a.kv_sb, a.kv_sl, a.kv_sh) ||
         !make_map(enc, &tv, a.v, a.L, a.Hkv, a.B, a.kv_sb, a.kv_sl, a.kv_sh)) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled rejected the q/k/v layout");
@@ -658,7 +662,7 @@ int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, c
     AttnParams p;
     p.a = a;
     p.scale_log2 = a.scale * 1.4426950408889634f;
-    p.n_qpairs = (a.L + 2 * kBM - 1) / (2 * kBM);
+    p.n_qpairs = (a.Lq + 2 * kBM - 1) / (2 * kBM);
     p.dbg = g_attn_dbg;
     static bool attr_set = false;
     if (!attr_set) {

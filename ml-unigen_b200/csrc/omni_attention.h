@@ -10,6 +10,8 @@ struct AttnArgs {
     const void* q; const void* k; const void* v; void* out;
     const int32_t* pad_len; const int32_t* soi_idx;
     int B, L, Hq, Hkv;
+    int Lq;          // query / output rows per sequence (q and out are [B, Lq, Hq, D])
+    int q0;          // absolute sequence index of query row 0 (0 for full attention; soi_idx for suffix-only passes)
     float scale;
     int64_t q_sb, q_sl, q_sh;
     int64_t kv_sb, kv_sl, kv_sh;

@@ -154,17 +154,18 @@ int ug_export_noise(uint64_t philox_seed, uint64_t philox_offset, int64_t batch_
     return UG_OK;
 }
 
-int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* out,
-                           const int32_t* pad_len, const int32_t* soi_idx,
-                           int B, int L, int Hq, int Hkv, int D, float scale,
-                           int64_t q_stride_b, int64_t q_stride_l, int64_t q_stride_h,
-                           int64_t kv_stride_b, int64_t kv_stride_l, int64_t kv_stride_h,
-                           int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
-                           void* stream)
+int ug_omni_attention_rows_bf16(const void* q, const void* k, const void* v, void* out,
+                                const int32_t* pad_len, const int32_t* soi_idx,
+                                int B, int L, int Lq, int q_row_offset, int Hq, int Hkv, int D, float scale,
+                                int64_t q_stride_b, int64_t q_stride_l, int64_t q_stride_h,
+                                int64_t kv_stride_b, int64_t kv_stride_l, int64_t kv_stride_h,
+                                int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
+                                void* stream)
 {
     if (!q || !k || !v || !out || !pad_len || !soi_idx) return fail(UG_ERR_NULL, "ug_omni_attention_bf16: null pointer");
-    if (D != 128 || Hkv < 1 || Hq % Hkv != 0 || B < 1 || L < 1)
-        return fail(UG_ERR_SHAPE, "ug_omni_attention_bf16: B=%d L=%d Hq=%d Hkv=%d D=%d unsupported (D=128, Hq%%Hkv==0)", B, L, Hq, Hkv, D);
+    if (D != 128 || Hkv < 1 || Hq % Hkv != 0 || B < 1 || L < 1 || Lq < 1 || q_row_offset < 0 || q_row_offset + Lq > L)
+        return fail(UG_ERR_SHAPE, "ug_omni_attention_bf16: B=%d L=%d Lq=%d q0=%d Hq=%d Hkv=%d D=%d unsupported (D=128, Hq%%Hkv==0, q0+Lq<=L)",
+                    B, L, Lq, q_row_offset, Hq, Hkv, D);
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out) ||
         ((q_stride_b | q_stride_l | q_stride_h | kv_stride_b | kv_stride_l | kv_stride_h | o_stride_b | o_stride_l | o_stride_h) & 7))
         return fail(UG_ERR_ALIGN, "ug_omni_attention_bf16: bases must be 16-byte aligned and strides multiples of 8 elements");
@@ -175,6 +176,7 @@ int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* ou
     a.q = q; a.k = k; a.v = v; a.out = out;
     a.pad_len = pad_len; a.soi_idx = soi_idx;
     a.B = B; a.L = L; a.Hq = Hq; a.Hkv = Hkv; a.scale = scale;
+    a.Lq = Lq; a.q0 = q_row_offset;
     a.q_sb = q_stride_b; a.q_sl = q_stride_l; a.q_sh = q_stride_h;
     a.kv_sb = kv_stride_b; a.kv_sl = kv_stride_l; a.kv_sh = kv_stride_h;
     a.o_sb = o_stride_b; a.o_sl = o_stride_l; a.o_sh = o_stride_h;
@@ -182,6 +184,19 @@ int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* ou
     int rc = ugk::launch_omni_attention(a, sms, static_cast<cudaStream_t>(stream), msg, sizeof msg);
     if (rc != 0) { snprintf(g_err, sizeof g_err, "ug_omni_attention_bf16: %s", msg); return rc; }
     return UG_OK;
+}
+
+int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* out,
+                           const int32_t* pad_len, const int32_t* soi_idx,
+                           int B, int L, int Hq, int Hkv, int D, float scale,
+                           int64_t q_stride_b, int64_t q_stride_l, int64_t q_stride_h,
+                           int64_t kv_stride_b, int64_t kv_stride_l, int64_t kv_stride_h,
+                           int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
+                           void* stream)
+{
+    return ug_omni_attention_rows_bf16(q, k, v, out, pad_len, soi_idx, B, L, L, 0, Hq, Hkv, D, scale, q_stride_b, q_stride_l,
+                                       q_stride_h, kv_stride_b, kv_stride_l, kv_stride_h, o_stride_b, o_stride_l, o_stride_h,
+                                       stream);
 }
 
 }  // extern "C"

@@ -108,12 +108,13 @@ def export_noise(seed: int, offset: int, B: int, N: int, V: int, device, batch_o
 
 
 def omni_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_len: torch.Tensor,
-                   soi_idx: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Omni attention.  q [B,L,Hq,D], k/v [B,L,Hkv,D] bf16 (last dim contiguous, arbitrary other
-    strides); pad_len / soi_idx int32 [B].  Returns out [B,L,Hq,D] bf16."""
+                   soi_idx: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None, q_offset: int = 0) -> torch.Tensor:
+    """Omni attention.  q [B,Lq,Hq,D], k/v [B,L,Hkv,D] bf16 (last dim contiguous, arbitrary other strides);
+    pad_len / soi_idx int32 [B].  Query row r is sequence row q_offset + r (Lq = L, q_offset = 0 for the full
+    pass; q_offset = soi_idx for the image-block-only pass of the prefix K/V reuse).  Returns out [B,Lq,Hq,D] bf16."""
     _need_cuda(q, k, v, pad_len, soi_idx)
-    B, L, Hq, D = q.shape
-    Hkv = k.shape[2]
+    B, Lq, Hq, D = q.shape
+    L, Hkv = k.shape[1], k.shape[2]
     if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
         raise ValueError("q, k, v must be bf16")
     if q.stride(3) != 1 or k.stride(3) != 1 or v.stride(3) != 1:
@@ -123,10 +124,10 @@ def omni_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_len: t
     if pad_len.dtype != torch.int32 or soi_idx.dtype != torch.int32:
         raise ValueError("pad_len / soi_idx must be int32")
     if out is None:
-        out = torch.empty(B, L, Hq, D, dtype=torch.bfloat16, device=q.device)
-    rc = _lib.lib().ug_omni_attention_bf16(
+        out = torch.empty(B, Lq, Hq, D, dtype=torch.bfloat16, device=q.device)
+    rc = _lib.lib().ug_omni_attention_rows_bf16(
         _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(pad_len), _ptr(soi_idx),
-        B, L, Hq, Hkv, D, float(scale),
+        B, L, Lq, int(q_offset), Hq, Hkv, D, float(scale),
         q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
         out.stride(0), out.stride(1), out.stride(2), _stream())
     _lib.check(rc)

@@ -125,14 +125,27 @@ class UniGenB200:
         sel_prob = torch.empty(B, N, dtype=torch.float32, device=self.device)
         img_rows = slice(L - N - 1, L - 1)
         temp = float(temperature)
+        # Text-prefix K/V reuse: when every sequence has its <|soi|> at the same index s0 (always the case for
+        # t2i_gen_prompt batches, which are left-padded to one length), rows < s0 are computed once (step 0) and
+        # only the N+2 rows of the image block go through the backbone in the later steps.
+        s0 = None
+        if kwargs.get("prefix_reuse", True) and timesteps > 1:
+            smin, smax = int(S.min()), int(S.max())                     # one host sync per generation
+            if smin == smax and smin == L - N - 2:
+                s0 = smin
+        kv_cache = bb.new_kv_cache(tokens.shape[0], L) if s0 is not None else None
         for step in range(timesteps):
             # tokens of the image block: mask id stays, codebook id c becomes c + text_vocab (unigen.py:451)
             img_tok = torch.where(ids_img == mask_id, ids_img, ids_img + text_vocab_size)
             tokens[:B, img_rows] = img_tok
             if use_cfg:
                 tokens[B:, img_rows] = img_tok
-            x = bb.embed_tokens(tokens)
-            hidden = bb.forward(x, P, S, rows=img_rows)                  # bf16 [B(2B), N, H]
+            if s0 is None or step == 0:
+                x = bb.embed_tokens(tokens)
+                hidden = bb.forward(x, P, S, rows=img_rows, kv_cache=kv_cache)        # bf16 [B(2B), N, H]
+            else:
+                x = bb.embed_tokens(tokens[:, s0:].contiguous())
+                hidden = bb.forward_suffix(x, P, S, s0, kv_cache, rows=slice(1, 1 + N))
             logits = bb.codebook_logits(hidden, text_vocab_size, V)      # bf16 [B(2B), N, V]
             ratio = 1.0 * (step + 1) / timesteps                        # unigen.py:425
             mask_ratio = noise_schedule(torch.tensor(ratio))             # unigen.py:426 (0-d CPU tensor)

@@ -135,6 +135,15 @@ def test_t2i_generate_loop_replays_through_oracle(dev, golden_dir):
     out2 = model.t2i_generate(input_ids=ids, attention_mask=dense, timesteps=T, noise_schedule=sampling.cosine_schedule,
                               image_token_num_per_image=N_IMG, text_vocab_size=TEXT_VOCAB, philox_seed=77, philox_offset=off0)
     assert torch.equal(out, out2)
+    # text-prefix K/V reuse on (default) vs off: same logits up to GEMM-shape rounding, hence (for this seed) same images
+    tr_off = []
+    out_off = model.t2i_generate(input_ids=ids, timesteps=T, image_token_num_per_image=N_IMG, text_vocab_size=TEXT_VOCAB,
+                                 philox_seed=77, philox_offset=off0, prefix_reuse=False, trace=tr_off)
+    for a, b in zip(trace, tr_off):
+        if torch.equal(a["ids_after"], b["ids_after"]):
+            d = (a["logits"].float() - b["logits"].float()).abs().max().item()
+            assert d <= 0.05 * a["logits"].float().abs().max().item(), d
+    _replay(tr_off, ids0, mask_id, seed=77)
     # sharding invariance: image 2 generated alone with batch_offset=2
     out3 = model.t2i_generate(input_ids=ids[2:], timesteps=T, image_token_num_per_image=N_IMG, text_vocab_size=TEXT_VOCAB,
                               philox_seed=77, philox_offset=off0, batch_offset=2)

@@ -134,3 +134,18 @@ def test_rejects_unsupported_shapes(dev):
     with pytest.raises(_lib.UnigenB200Error):
         ops.omni_attention(q, q, q, torch.zeros(1, dtype=torch.int32, device=dev),
                            torch.zeros(1, dtype=torch.int32, device=dev), 1.0)
+
+
+def test_query_row_window_equals_full_attention_rows(dev):
+    """ug_omni_attention_rows_bf16 (image-block rows only, the prefix K/V reuse pass) returns exactly the rows the
+    full pass returns -- each query row sees the same kv tiles in the same order."""
+    from ml_unigen_b200 import ops
+    B, L, Hq, Hkv, D = 3, 1163, 12, 2, 128
+    q, k, v = _mk(B, L, Hq, Hkv, D, seed=3, dev=dev)
+    Pt = torch.tensor([0, 57, 99], dtype=torch.int32, device=dev)
+    St = torch.full((B,), 137, dtype=torch.int32, device=dev)
+    full = ops.omni_attention(q, k, v, Pt, St, D ** -0.5)
+    for s0 in (137, 128, 500):
+        part = ops.omni_attention(q[:, s0:], k, v, Pt, St, D ** -0.5, q_offset=s0)
+        assert part.shape == (B, L - s0, Hq, D)
+        assert torch.equal(part, full[:, s0:]), f"row window s0={s0} differs from the full pass"
