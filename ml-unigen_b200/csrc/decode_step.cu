@@ -17,9 +17,11 @@
 //     win if byte <= 256*16*p_i, so on average ~48 of 8192 elements are evaluated exactly
 //     (two IEEE divisions + the fine noise bits).  If the best candidate does not clear the
 //     bound 1/16 (probability e^-16 per row) the whole row is evaluated exactly;
-//   * the last CTA to finish a row of image b (device-scope counter) computes the N
-//     confidences, finds the mask_len-th smallest with a 4-pass radix select in shared memory
-//     and writes mask / ids in place -- no second launch, no host synchronisation.
+//   * every finished row is published as ONE 64-bit word (id+1 | selected probability; 0 = pending), so no
+//     fence or atomic is needed; the CTA that processed the last row of image b gathers the N words
+//     (spinning on the few still in flight), computes the confidences, finds the mask_len-th smallest
+//     with a 4-pass radix select in shared memory and writes mask / ids in place -- no second launch,
+//     no host synchronisation.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cfloat>
@@ -84,6 +86,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long best_key(float r, int i)
+{
+    return ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);   // r >= 0
+}
 __device__ __forceinline__ float4 ld_stream_f4(const float* p)
 {
     float4 r;
@@ -103,18 +115,6 @@ __device__ __forceinline__ void best_merge(Best& a, float r, float p, int i)
 {
     if (r > a.r || (r == a.r && i < a.i)) { a.r = r; a.p = p; a.i = i; }
 }
-__device__ __forceinline__ Best best_warp(Best b)
-{
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        float r = __shfl_xor_sync(0xffffffffu, b.r, off);
-        float p = __shfl_xor_sync(0xffffffffu, b.p, off);
-        int i = __shfl_xor_sync(0xffffffffu, b.i, off);
-        best_merge(b, r, p, i);
-    }
-    return b;
-}
-
 // exact evaluation of one element of the race (cold path: kept out of line on purpose)
 __device__ __noinline__ void race_eval_exact(float ek, float S, uint32_t coarse, int i, uint64_t rowg, uint64_t seed,
                                              uint64_t offset, Best& best)
@@ -133,11 +133,8 @@ struct Ctrl {
     float red_max[8];
     float red_min[8];
     float red_sum[8];
-    float red_r[8];
-    float red_p[8];
-    int red_i[8];
+    unsigned long long best;     // max over candidates of (ratio bits << 32 | ~index)
     int cand_cnt;
-    int sel_b;
     int sel_unknown;
     int sel_bin;
     int sel_k;
@@ -157,18 +154,30 @@ __device__ void select_phase(const DecodeArgs& a, int b, Ctrl* c, uint32_t* keys
     const int lane = tid & 31, warp = tid >> 5;
     const uint64_t gb = (uint64_t)(a.batch_offset + b);
     const size_t base = (size_t)b * N;
-    __threadfence();
     if (tid == 0) c->sel_unknown = 0;
     consumer_bar();
     int unk = 0;
     for (int n = tid; n < N; n += kConsumers) {
-        float psel = __ldcg(a.psel + base + n);
+        float psel;
+        if (mask_len_in) {
+            psel = a.psel[base + n];
+        } else {
+            // rows of this image still in flight on other CTAs are published within a row time
+            unsigned long long w;
+            uint32_t spins = 0;
+            while ((w = ld_relaxed_u64(a.slots + base + n)) == 0ull) {
+                if (++spins > (1u << 26)) __trap();
+            }
+            a.slots[base + n] = 0ull;                                  // re-arm the workspace for the next launch
+            psel = __uint_as_float((uint32_t)w);
+            a.sampled[base + n] = (long long)(w >> 32) - 1;            // models/unigen.py:419-422
+            unk += (a.ids[base + n] == a.mask_id);
+        }
         float u = a.u_noise ? a.u_noise[base + n] : ug::select_u((uint32_t)n, gb, a.seed, a.offset);
         float conf = ug::confidence(psel, u, a.temperature);
         keys[n] = ug::ordered_key(conf);
         if (a.conf_out) a.conf_out[base + n] = conf;
         if (a.sel_prob_out) a.sel_prob_out[base + n] = psel;
-        if (!mask_len_in) unk += (a.ids[base + n] == a.mask_id);
     }
     if (!mask_len_in) {
         unk = __reduce_add_sync(0xffffffffu, unk);
@@ -218,12 +227,8 @@ __device__ void select_phase(const DecodeArgs& a, int b, Ctrl* c, uint32_t* keys
     for (int n = tid; n < N; n += kConsumers) {
         uint8_t masking = keys[n] < cut;                // models/sampling.py:45 (strict <)
         a.mask[base + n] = masking;
-        if (!mask_len_in) {
-            long long s = __ldcg((const long long*)a.sampled + base + n);
-            a.ids[base + n] = masking ? a.mask_id : s;  // models/unigen.py:453
-        }
+        if (!mask_len_in) a.ids[base + n] = masking ? a.mask_id : a.sampled[base + n];   // models/unigen.py:453 (same thread wrote sampled)
     }
-    if (tid == 0 && a.counters) a.counters[b] = 0u;
     consumer_bar();
 }
 
@@ -267,12 +272,9 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
             if (valid) cur = a.ids[r];
             const bool unknown = valid && cur == a.mask_id;
             bool completes = false;
-            if (valid && !unknown) {                              // models/unigen.py:422, 433
-                a.sampled[r] = cur;
-                a.psel[r] = FLT_MAX;
-                __threadfence();
-                const int b = (int)(r / N);
-                completes = atomicAdd(&a.counters[b], 1u) == (unsigned)(N - 1);
+            if (valid && !unknown) {                              // models/unigen.py:422, 433: keep the id, confidence = FLT_MAX
+                a.slots[r] = ((unsigned long long)(cur + 1) << 32) | (unsigned long long)__float_as_uint(FLT_MAX);
+                completes = (r % N) == N - 1;                     // the image's last row needs no consumer: schedule its selection
             }
             unsigned umask = __ballot_sync(0xffffffffu, unknown);
             unsigned cmask = __ballot_sync(0xffffffffu, completes);
@@ -318,16 +320,12 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
     // =============================================================== consumers (256 threads)
     int stage = 0;
     uint32_t phase = 0;
-    int pending_sel = -1;            // thread 0: image whose last row this CTA published (checked one barrier later)
     while (true) {
         mbar_wait(&c->full[stage], phase);
         const int task = c->task[stage];
-        if (tid == 0) { c->sel_b = pending_sel; pending_sel = -1; }
         if (task < 0) {                                            // sentinel (-1) or SELECT(b) (<= -2)
             consumer_bar();
             if (tid == 0) mbar_arrive(&c->empty[stage]);
-            const int sb = c->sel_b;
-            if (sb >= 0) select_phase(a, sb, c, keys, tid, nullptr);
             if (task == -1) break;
             select_phase(a, -2 - task, c, keys, tid, nullptr);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -387,11 +385,7 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
             if (lane == 0) { c->red_max[warp] = fmx; c->red_min[warp] = fmn; }
         }
         consumer_bar();                                            // (1)
-        {
-            const int sb = c->sel_b;                               // image completed by this CTA's previous row?
-            if (sb >= 0) select_phase(a, sb, c, keys, tid, nullptr);
-        }
-        if (tid == 0) c->cand_cnt = 0;
+        if (tid == 0) { c->cand_cnt = 0; c->best = 0ull; }
         float m = c->red_max[0], mn = c->red_min[0];
 #pragma unroll
         for (int w = 1; w < 8; ++w) { m = fmaxf(m, c->red_max[w]); mn = fminf(mn, c->red_min[w]); }
@@ -499,18 +493,15 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
                 best_merge(best, r, p, i);
             }
         }
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            Best wb = best_warp(best);
-            if (lane == 0) { c->red_r[warp] = wb.r; c->red_p[warp] = wb.p; c->red_i[warp] = wb.i; }
-            consumer_bar();                                        // (4)
-            best = Best{c->red_r[0], c->red_p[0], c->red_i[0]};
-#pragma unroll
-            for (int w = 1; w < 8; ++w) best_merge(best, c->red_r[w], c->red_p[w], c->red_i[w]);
-            if (kInjectQ || pass == 1) break;
-            if (!need_full && best.r >= kRaceBound) break;
-            // rare: no candidate clears the bound -> evaluate every element of the row exactly
+        // ---- block argmax: one 64-bit shared atomicMax per thread that holds a candidate
+        unsigned long long mykey = best.r >= 0.0f ? best_key(best.r, best.i) : 0ull;
+        if (mykey) atomicMax(&c->best, mykey);
+        consumer_bar();                                            // (4)
+        unsigned long long win = c->best;
+        if (!kInjectQ && (need_full || __uint_as_float((uint32_t)(win >> 32)) < kRaceBound)) {
+            // rare (e^-16 per row): no candidate clears the bound -> evaluate every element of the row exactly
             consumer_bar();
+            if (tid == 0) c->best = 0ull;
             best = Best{-1.0f, 0.0f, 0x7fffffff};
 #pragma unroll
             for (int ch = 0; ch < kChunks; ++ch) {
@@ -520,18 +511,20 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
                 for (int k = 0; k < kVec; ++k)
                     race_eval_exact(e[ch * kVec + k], S, ug::coarse_byte(cb, k), i0 + k, rowg, a.seed, a.offset, best);
             }
+            consumer_bar();
+            mykey = best_key(best.r, best.i);
+            atomicMax(&c->best, mykey);
+            consumer_bar();
+            win = c->best;
         }
-        // ---- publish the row (the ring slot is free now).  Whether this row completed image b is known
-        //      only when the device-scope atomic returns; the CTA acts on it after its next barrier.
-        if (tid == 0) {
-            mbar_arrive(&c->empty[stage]);
-            a.sampled[row] = best.i;                               // models/unigen.py:419-422
-            a.psel[row] = best.p;                                  // models/unigen.py:429-430
+        // ---- publish: the thread that holds the winner writes one word (id+1 | selected probability); the ring
+        //      slot is free now.  The CTA that processed the last row of an image runs that image's mask selection.
+        if (mykey == win && mykey) {
+            a.slots[row] = ((unsigned long long)(best.i + 1) << 32) | (unsigned long long)__float_as_uint(best.p);
             if (a.rowsum_out) a.rowsum_out[row] = S;
-            __threadfence();
-            const unsigned old = atomicAdd(&a.counters[b], 1u);
-            pending_sel = (old == (unsigned)(N - 1)) ? b : -1;
         }
+        if (tid == 0) mbar_arrive(&c->empty[stage]);
+        if (row - (long long)b * N == N - 1) select_phase(a, b, c, keys, tid, nullptr);
         if (++stage == stages) { stage = 0; phase ^= 1u; }
     }
 }

@@ -25,8 +25,8 @@ struct DecodeArgs {
     float temperature;
     int force_full_race;         // test hook: skip the candidate filter, evaluate every element
     // workspace
-    float* psel;                 // [B*N] selected probabilities (FLT_MAX = known)
-    unsigned* counters;          // [B] rows finished per image
+    float* psel;                 // standalone top-k only: probs [B*N]
+    unsigned long long* slots;   // [B*N] one word per row: (id + 1) << 32 | bits(selected prob); 0 = not published yet
     unsigned* ticket;            // row-pair ticket
     unsigned* cta_done;          // producers finished
 };

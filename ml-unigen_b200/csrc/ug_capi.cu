@@ -62,8 +62,8 @@ size_t ug_decode_step_workspace_bytes(int B, int N, int V)
 {
     (void)V;
     if (B <= 0 || N <= 0) return 0;
-    // [counters B][ticket][cta_done] padded to 256 B, then psel float[B*N]
-    return align_up(sizeof(unsigned) * ((size_t)B + 2), 256) + sizeof(float) * (size_t)B * N;
+    // [ticket][cta_done] padded to 256 B, then one 64-bit result word per row
+    return 256 + sizeof(unsigned long long) * (size_t)B * N;
 }
 
 int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float guidance_scale,
@@ -111,10 +111,9 @@ int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float gui
     a.cap = mask_len_cap;
     a.temperature = temperature;
     unsigned* w = static_cast<unsigned*>(workspace);
-    a.counters = w;
-    a.ticket = w + B;
-    a.cta_done = w + B + 1;
-    a.psel = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up(sizeof(unsigned) * ((size_t)B + 2), 256));
+    a.ticket = w;
+    a.cta_done = w + 1;
+    a.slots = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + 256);
     cudaError_t e = ugk::launch_decode_step(a, sms, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "ug_decode_step_bf16 launch");
     return UG_OK;

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported(built_lib):
 
 def test_abi_version_and_workspace(built_lib):
     assert built_lib.ug_abi_version() == 1
-    assert built_lib.ug_decode_step_workspace_bytes(16, 1024, 8192) >= 16 * 1024 * 4
+    assert built_lib.ug_decode_step_workspace_bytes(16, 1024, 8192) >= 16 * 1024 * 8
     assert built_lib.ug_decode_step_workspace_bytes(0, 1024, 8192) == 0
 
 
