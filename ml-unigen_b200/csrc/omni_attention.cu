@@ -81,9 +81,12 @@ __device__ __forceinline__ void turn_wait(int id) { asm volatile("bar.sync %0, 2
 __device__ __forceinline__ void turn_pass(int id) { asm volatile("bar.arrive %0, 256;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// executed by the whole (converged) MMA warp; one elected lane commits
 __device__ __forceinline__ void tc_commit(uint64_t* bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(s_u32(bar))
+                 : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
@@ -185,6 +188,32 @@ struct AttnParams {
     float* dbg;             // optional: dumps S and P of (b=0, h=0, q tile 0, kv tile 0)
 };
 
+// Descriptor words.  The high word of every shared-memory descriptor used here is the same constant
+// (SBO = 1024 B, version 1, SWIZZLE_128B); the low word is (address >> 4) | (LBO >> 4) << 16, so stepping through
+// a tile is one 32-bit add on the low word -- the single issuing thread must not spend ~100 dependent cycles of
+// 64-bit arithmetic per MMA (measured: that, not the tensor core, was pacing the first versions of this kernel).
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_kmajor(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_mnmajor(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | ((kPanelBytes >> 4) << 16); }
+// These wrappers are executed by ALL 32 lanes of the (converged) MMA warp; elect.sync picks the one lane that
+// issues.  Issuing from inside an `if (lane == 0)` region instead makes ptxas wrap every UTCHMMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop (operands must be uniform registers), which costs more than the MMA.
+__device__ __forceinline__ void tc_mma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 db, {%2, %5};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+}
 // TS form: A operand (P, bf16 pairs) read from tensor memory, B from shared memory
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
@@ -305,8 +334,9 @@ struct Attn2Bars {
     uint64_t q_full;
     uint64_t k_full[kKVStages], k_empty[kKVStages];
     uint64_t v_full[kKVStages], v_empty[kKVStages];
-    uint64_t s_full[2];          // per query tile: S = Q K^T landed in TMEM (tcgen05.commit)
-    uint64_t p_full[2];          // per query tile: P written to TMEM by the 128 softmax threads
+    uint64_t s_full[2][2];       // [tile][half]: 64 score columns landed in TMEM (tcgen05.commit)
+    uint64_t p_full[2][2];       // [tile][half]: 64 probability columns written to TMEM by the 128 softmax threads
+    uint64_t pv_done[2];         // per query tile: one phase per accumulated P V half (O may be rescaled after it)
     uint64_t o_done[2];          // per query tile: last P V accumulated
     uint32_t tmem_base;
 };
@@ -341,6 +371,14 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     if (hasB) kv_range(iB, min(iB + kBM, iEnd), P, S, L, tB0, tB1);
     const int tU0 = hasB ? min(tA0, tB0) : tA0;
     const int tU1 = hasB ? max(tA1, tB1) : tA1;
+    // union [jlo, jhi) of the allowed kv columns over the rows of each tile: a 64-column half outside it is skipped
+    const int jloA = (iA < P) ? 0 : P, jhiA = (min(iA + kBM, iEnd) > S) ? L : min(iA + kBM, iEnd);
+    const int jloB = (iB < P) ? 0 : P, jhiB = (min(iB + kBM, iEnd) > S) ? L : min(iB + kBM, iEnd);
+    auto half_on = [&](int x, int t, int hf) -> bool {
+        const bool tile_on = x == 0 ? (t >= tA0 && t < tA1) : (hasB && t >= tB0 && t < tB1);
+        const int c0 = t * kBN + hf * 64;
+        return tile_on && c0 < (x == 0 ? jhiA : jhiB) && c0 + 64 > (x == 0 ? jloA : jloB);
+    };
 
     if (tid == 0) {
         bar_init(&bars->q_full, 1);
@@ -348,7 +386,11 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             bar_init(&bars->k_full[s], 1); bar_init(&bars->k_empty[s], 1);
             bar_init(&bars->v_full[s], 1); bar_init(&bars->v_empty[s], 1);
         }
-        for (int x = 0; x < 2; ++x) { bar_init(&bars->s_full[x], 1); bar_init(&bars->p_full[x], 128); bar_init(&bars->o_done[x], 1); }
+        for (int x = 0; x < 2; ++x) {
+            for (int hf = 0; hf < 2; ++hf) { bar_init(&bars->s_full[x][hf], 1); bar_init(&bars->p_full[x][hf], 128); }
+            bar_init(&bars->o_done[x], 1);
+            bar_init(&bars->pv_done[x], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {       // TMEM: all 512 columns (one CTA per SM)
@@ -395,74 +437,93 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
     } else if (warp == 9) {
         // =========================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = make_idesc(kBM, kBN, 0, 0);
-            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);
+        // Each query tile is pipelined in two 64-column halves: while a warpgroup is in the softmax of one half the
+        // tensor core computes the other half's P V and the next tile's Q K^T for the half just released, so the
+        // softmax warps and the tensor core both stay busy.  Slot order per kv tile: (A,0) (B,0) (A,1) (B,1); in
+        // each slot: O_x += P_x[half] V_t[half]  then  S_x[half] = Q_x K_(t+1)[half]^T.
+        {
+            constexpr uint32_t idesc_qk = make_idesc(kBM, 64, 0, 0);        // S half: M=128, N=64
+            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);        // O:      M=128, N=128, K=64 per half
             const uint32_t qa_addr = s_u32(smem + kOff2QA), qb_addr = s_u32(smem + kOff2QB);
-            int np[2] = {0, 0};                              // P tiles consumed per query tile (phase of p_full)
-            auto in_range = [&](int x, int t) { return x == 0 ? (t >= tA0 && t < tA1) : (hasB && t >= tB0 && t < tB1); };
-            // S_x = Q_x K_t^T ; signals s_full[x]; the LAST QK of a kv tile also frees its K slot
-            auto issue_qk = [&](int x, int t) {
+            int np[2][2] = {{0, 0}, {0, 0}};                 // P halves consumed (phase of p_full)
+            bool o_started[2] = {false, false};
+            const uint32_t q_lo[2] = {desc_lo_kmajor(qa_addr), desc_lo_kmajor(qb_addr)};
+            const uint32_t k_lo0 = desc_lo_kmajor(s_u32(smem + kOff2K)), v_lo0 = desc_lo_mnmajor(s_u32(smem + kOff2V));
+            auto issue_qk = [&](int x, int t, int hf) {
                 const int j = t - tU0, s = j % kKVStages;
-                const uint32_t k_addr = s_u32(smem + kOff2K + s * kTileBytes);
-                const uint32_t q_addr = x == 0 ? qa_addr : qb_addr;
+                // K tile: two 64-wide d panels of [128 kv rows x 128 B]; kv rows 64*hf.. start 8 KB into each panel
+                const uint32_t kl = k_lo0 + (uint32_t)s * (kTileBytes >> 4) + (uint32_t)hf * ((64u * 128u) >> 4);
+                const uint32_t ql = q_lo[x];
+                const uint32_t d = tmem + (uint32_t)x * 128u + (uint32_t)hf * 64u;
 #pragma unroll
                 for (int k = 0; k < kD / 16; ++k) {
-                    const uint32_t off = (uint32_t)(k >> 2) * kPanelBytes + (uint32_t)(k & 3) * 32u;
-                    tc_mma(tmem + (uint32_t)x * 128u, desc_kmajor(q_addr + off), desc_kmajor(k_addr + off), idesc_qk, k > 0);
+                    // 16 bf16 along d = 32 bytes inside the 128-byte swizzle row; panel switch at k = 4
+                    constexpr uint32_t dummy = 0; (void)dummy;
+                    const uint32_t off = (uint32_t)(k >> 2) * (kPanelBytes >> 4) + (uint32_t)(k & 3) * 2u;
+                    tc_mma_ss_lo(d, ql + off, kl + off, idesc_qk, k > 0 ? 1u : 0u);
                 }
-                tc_commit(&bars->s_full[x]);
+                tc_commit(&bars->s_full[x][hf]);
             };
-            auto qk_pair = [&](int t) {                      // both query tiles against kv tile t
+            auto wait_k = [&](int t) {
                 const int j = t - tU0, s = j % kKVStages;
                 bar_wait(&bars->k_full[s], (uint32_t)(j / kKVStages) & 1u);
                 tc_fence_after();
                 return s;
             };
+            auto last_pv = [&](int x, int t, int hf) {        // is (t, hf) the last half this tile accumulates?
+                for (int hh = hf + 1; hh < 2; ++hh) if (half_on(x, t, hh)) return false;
+                for (int tt = t + 1; tt < tU1; ++tt) for (int hh = 0; hh < 2; ++hh) if (half_on(x, tt, hh)) return false;
+                return true;
+            };
             bar_wait(&bars->q_full, 0);
-            // prologue: scores of the first kv tile
-            {
-                const int s = qk_pair(tU0);
-                if (in_range(0, tU0)) issue_qk(0, tU0);
-                if (in_range(1, tU0)) issue_qk(1, tU0);
+            {   // prologue: scores of the first kv tile
+                const int s = wait_k(tU0);
+                for (int hf = 0; hf < 2; ++hf)
+                    for (int x = 0; x < 2; ++x)
+                        if (half_on(x, tU0, hf)) issue_qk(x, tU0, hf);
                 tc_commit(&bars->k_empty[s]);
             }
             for (int t = tU0; t < tU1; ++t) {
                 const int j = t - tU0, s = j % kKVStages;
                 const bool next = t + 1 < tU1;
                 int sn = 0;
-                bool v_ready = false;
+                bool v_ready = false, k_ready = false;
+                for (int hf = 0; hf < 2; ++hf) {
+                    for (int x = 0; x < 2; ++x) {
+                        if (half_on(x, t, hf)) {
+                            if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 0);
+                            bar_wait(&bars->p_full[x][hf], (uint32_t)np[x][hf] & 1u);
+                            if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 1);
+                            if (!v_ready) { bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u); v_ready = true; }
+                            tc_fence_after();
+                            // V tile rows 64*hf.. (MN-major): 16 kv rows per MMA
+                            const uint32_t vl = v_lo0 + (uint32_t)s * (kTileBytes >> 4) + (uint32_t)hf * ((64u * 128u) >> 4);
+                            const uint32_t p_tmem = tmem + (uint32_t)x * 128u + (uint32_t)hf * 64u;      // P half aliases its S half
+                            const uint32_t o_tmem = tmem + 256u + (uint32_t)x * 128u;
+                            const uint32_t acc0 = o_started[x] ? 1u : 0u;
 #pragma unroll
-                for (int x = 0; x < 2; ++x) {
-                    if (in_range(x, t)) {
-                        // O_x (+)= P_x V_t  once the softmax warpgroup x has written P_x
-                        UG_TL(2, 2 * j + x, 0);
-                        bar_wait(&bars->p_full[x], (uint32_t)np[x] & 1u);
-                        UG_TL(2, 2 * j + x, 1);
-                        if (!v_ready) { bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u); v_ready = true; }
-                        tc_fence_after();
-                        const uint32_t v_addr = s_u32(smem + kOff2V + s * kTileBytes);
-                        const int first_t = x == 0 ? tA0 : tB0;
-#pragma unroll
-                        for (int k = 0; k < kBN / 16; ++k)
-                            tc_mma_ts(tmem + 256u + (uint32_t)x * 128u, tmem + (uint32_t)x * 128u + (uint32_t)k * 8u,
-                                      desc_mnmajor(v_addr + (uint32_t)k * 16u * 128u), idesc_pv, (t > first_t || k > 0) ? 1u : 0u);
-                        ++np[x];
-                        UG_TL(2, 2 * j + x, 2);
-                        const int last_t = (x == 0 ? tA1 : tB1) - 1;
-                        if (t == last_t) tc_commit(&bars->o_done[x]);
-                    }
-                    // scores of the next kv tile for the same query tile go right behind (keeps the tensor core busy
-                    // while the other warpgroup is still in its softmax)
-                    if (next) {
-                        if (x == 0) sn = qk_pair(t + 1);
-                        if (in_range(x, t + 1)) issue_qk(x, t + 1);
-                        UG_TL(2, 2 * j + x, 3);
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_ts_lo(o_tmem, p_tmem + (uint32_t)k * 8u, vl + (uint32_t)k * ((16u * 128u) >> 4), idesc_pv,
+                                             k > 0 ? 1u : acc0);
+                            tc_commit(&bars->pv_done[x]);
+                            o_started[x] = true;
+                            ++np[x][hf];
+                            if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 2);
+                            if (last_pv(x, t, hf)) tc_commit(&bars->o_done[x]);
+                        }
+                        if (next && half_on(x, t + 1, hf)) {
+                            if (!k_ready) { sn = wait_k(t + 1); k_ready = true; }
+                            issue_qk(x, t + 1, hf);
+                            if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 3);
+                        }
                     }
                 }
-                if (!v_ready) { bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u); }
+                if (!v_ready) bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u);
                 tc_commit(&bars->v_empty[s]);
-                if (next) tc_commit(&bars->k_empty[sn]);
+                if (next) {
+                    if (!k_ready) sn = wait_k(t + 1);
+                    tc_commit(&bars->k_empty[sn]);
+                }
             }
         }
     } else {
@@ -491,49 +552,40 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             float l_run = 0.0f;
             const bool dump = p.dbg && x == 0 && qp == 0 && h == 0 && b == 0;
 
-            const bool turns = hasB && (UG_ATTN_TURNS != 0);   // both warpgroups alive: alternate, tile A first
-            if (turns && x == 1) turn_pass(2);
-            for (int t = tU0; t < tU1; ++t) {
-                const bool mine = t >= t0 && t < t1;
-                if (!mine) {                             // keep the alternation going while the other tile still has work
-                    if (turns) { turn_wait(2 + x); turn_pass(3 - x); }
-                    continue;
-                }
-                const int n = t - t0;
-                const int j0 = t * kBN;
-                const bool full_tile = (j0 >= max_lo) && (j0 + kBN <= min_hi);
+            int ns[2] = {0, 0};                           // halves processed (phase of s_full)
+            int n_pub = 0;                                // P halves published so far by this warpgroup
+            bool o_live = false;                          // O_x holds (or is about to hold) an accumulation
+            for (int t = t0; t < t1; ++t) {
+              for (int hf = 0; hf < 2; ++hf) {
+                if (!half_on(x, t, hf)) continue;
+                const int n = 2 * (t - t0) + hf;
+                const int j0 = t * kBN + hf * 64;
+                const bool full_tile = (j0 >= max_lo) && (j0 + 64 <= min_hi);
                 const int clo = lo - j0, chi = hi - j0;
+                const uint32_t sh_addr = s_addr + (uint32_t)hf * 64u;
                 if (r == 0) UG_TL(x, n, 0);
-                bar_wait(&bars->s_full[x], (uint32_t)n & 1u);
+                bar_wait(&bars->s_full[x][hf], (uint32_t)ns[hf] & 1u);
+                ++ns[hf];
                 tc_fence_after();
-                if (turns) turn_wait(2 + x);
                 if (r == 0) UG_TL(x, n, 1);
-                // the whole score row (128 fp32) comes to registers in one go: four loads in flight, one wait
-                uint32_t v0[32], v1[32], v2[32], v3[32];
-                tmem_ld32_async(s_addr, v0);
-                tmem_ld32_async(s_addr + 32, v1);
-                tmem_ld32_async(s_addr + 64, v2);
-                tmem_ld32_async(s_addr + 96, v3);
+                // 64 scores of this row come to registers: two loads in flight, one wait
+                uint32_t v0[32], v1[32];
+                tmem_ld32_async(sh_addr, v0);
+                tmem_ld32_async(sh_addr + 32, v1);
                 tmem_ld_wait();
-                pin32(v0); pin32(v1); pin32(v2); pin32(v3);
-                if (dump && n == 0)
+                pin32(v0); pin32(v1);
+                if (dump && t == t0)
                     for (int q = 0; q < 32; ++q) {
-                        p.dbg[r * 128 + q] = __uint_as_float(v0[q]);
-                        p.dbg[r * 128 + 32 + q] = __uint_as_float(v1[q]);
-                        p.dbg[r * 128 + 64 + q] = __uint_as_float(v2[q]);
-                        p.dbg[r * 128 + 96 + q] = __uint_as_float(v3[q]);
+                        p.dbg[r * 128 + hf * 64 + q] = __uint_as_float(v0[q]);
+                        p.dbg[r * 128 + hf * 64 + 32 + q] = __uint_as_float(v1[q]);
                     }
                 float mx = -INFINITY;
                 if (full_tile) {
                     mx = row_max_chunk<false>(v0, 0, clo, chi, mx);
                     mx = row_max_chunk<false>(v1, 32, clo, chi, mx);
-                    mx = row_max_chunk<false>(v2, 64, clo, chi, mx);
-                    mx = row_max_chunk<false>(v3, 96, clo, chi, mx);
                 } else {
                     mx = row_max_chunk<true>(v0, 0, clo, chi, mx);
                     mx = row_max_chunk<true>(v1, 32, clo, chi, mx);
-                    mx = row_max_chunk<true>(v2, 64, clo, chi, mx);
-                    mx = row_max_chunk<true>(v3, 96, clo, chi, mx);
                 }
                 if (r == 0) UG_TL(x, n, 2);
                 // lazy rescaling: keep m_ref while the true max stays within 2^tau of it (exact: O, l and P share m_ref)
@@ -542,8 +594,14 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 const float m_new = move ? m_true : m_ref;
                 const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
                 const float alpha = move ? ex2(m_ref - m_use) : 1.0f;          // 0 when m_ref was -inf
-                // S_x(t) complete implies P_x V_(t-1) complete (same issuing thread, in order): O_x can be rescaled now
-                if (n > 0 && __any_sync(0xffffffffu, move)) {
+                // O_x may only be rescaled when no P V of this tile is in flight.  These scores (half number n_pub of
+                // this tile) were issued behind the P V of half n_pub-2, so everything up to n_pub-2 is complete; only the
+                // P V of the half published just before can still be running: wait for its phase of pv_done (the barrier
+                // is at most one phase behind, so the parity wait is exact).  Rare: the max moves by > 2^8 only in the
+                // first tile or two of a row.
+                if (o_live && __any_sync(0xffffffffu, move)) {
+                    bar_wait(&bars->pv_done[x], (uint32_t)(n_pub - 1) & 1u);
+                    tc_fence_after();
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ++ch) {
                         uint32_t v[32];
@@ -554,33 +612,33 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     }
                 }
                 if (r == 0) UG_TL(x, n, 3);
-                // probabilities -> bf16 pairs -> P_x in tensor memory (A operand of the second GEMM)
+                // probabilities -> bf16 pairs -> P half in tensor memory (A operand of the second GEMM)
                 float rs = 0.0f;
                 {
                     uint32_t pk[16];
 #define UG_PROB_CHUNK(vv, ch)                                                                                     \
     rs += full_tile ? prob_chunk<false>(vv, pk, c, m_use, (ch) * 32, clo, chi)                                    \
                     : prob_chunk<true>(vv, pk, c, m_use, (ch) * 32, clo, chi);                                    \
-    if (dump && n == 0)                                                                                           \
+    if (dump && t == t0)                                                                                          \
         for (int q = 0; q < 16; ++q) {                                                                            \
-            p.dbg[16384 + r * 128 + (ch) * 32 + 2 * q] = __uint_as_float(pk[q] << 16);                            \
-            p.dbg[16384 + r * 128 + (ch) * 32 + 2 * q + 1] = __uint_as_float(pk[q] & 0xffff0000u);                \
+            p.dbg[16384 + r * 128 + hf * 64 + (ch) * 32 + 2 * q] = __uint_as_float(pk[q] << 16);                  \
+            p.dbg[16384 + r * 128 + hf * 64 + (ch) * 32 + 2 * q + 1] = __uint_as_float(pk[q] & 0xffff0000u);      \
         }                                                                                                         \
-    tmem_st16(s_addr + (ch) * 16, pk);
+    tmem_st16(sh_addr + (ch) * 16, pk);
                     UG_PROB_CHUNK(v0, 0)
                     UG_PROB_CHUNK(v1, 1)
-                    UG_PROB_CHUNK(v2, 2)
-                    UG_PROB_CHUNK(v3, 3)
 #undef UG_PROB_CHUNK
                 }
-                if (turns) turn_pass(3 - x);
                 tmem_st_wait();
                 if (r == 0) UG_TL(x, n, 4);
                 l_run = l_run * alpha + rs;
                 m_ref = m_new;
+                o_live = true;
+                ++n_pub;
                 tc_fence_before();
-                bar_arrive(&bars->p_full[x]);
+                bar_arrive(&bars->p_full[x][hf]);
                 if (r == 0) UG_TL(x, n, 5);
+              }
             }
             // epilogue: O / l -> bf16 -> global
             bar_wait(&bars->o_done[x], 0);
