@@ -233,23 +233,32 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 
 
-// 2^x for two values on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. error 7.5e-5 -- far
-// below the bf16 rounding of P): relieves the MUFU pipe, which is as loaded as the tensor core at head_dim 128.
+#ifndef UG_ATTN_POLY
+#define UG_ATTN_POLY 0       // of every 4 pairs of exponentials, how many go to the FMA pipe (polynomial); 0 = all on MUFU
+#endif
+#ifndef UG_ATTN_TURNS
+#define UG_ATTN_TURNS 0      // 1: the two softmax warpgroups alternate (named barriers), 0: free running
+#endif
+// 2^x for two values on the FMA pipe (round-to-nearest split x = n + f via the 1.5*2^23 constant, degree-3 minimax
+// polynomial for 2^f on [-0.5, 0.5] with relative error 7.5e-5 -- far below the bf16 rounding of P -- and an integer
+// add of n into the exponent).  MUFU.EX2 is the scarcest pipe of this kernel on B200 (measured ~16 cycles per warp
+// instruction: 128x128 exponentials per tile cost twice the tensor-core time of the two GEMMs), so most exponentials
+// are computed here and only a fraction goes to the MUFU.
 __device__ __forceinline__ float2 ex2_poly2(float2 x)
 {
-    const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
-    x.x = fmaxf(x.x, -120.0f);
-    x.y = fmaxf(x.y, -120.0f);
-    const float2 t = __fadd2_rn(x, magic);
-    const float2 n = __fadd2_rn(t, nmagic);
-    const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+    const float2 magic = make_float2(12582912.0f, 12582912.0f);
+    x.x = fmaxf(x.x, -125.0f);                                 // keeps the exponent arithmetic in range; 2^-125 ~ 0 for P
+    x.y = fmaxf(x.y, -125.0f);
+    const float2 t = __fadd2_rn(x, magic);                     // low mantissa bits of t hold n = rint(x)
+    const float2 nn = __fadd2_rn(magic, make_float2(-t.x, -t.y));   // -n
+    const float2 f = __fadd2_rn(x, nn);
     float2 p = make_float2(0x1.c3f76p-5f, 0x1.c3f76p-5f);
     p = __ffma2_rn(p, f, make_float2(0x1.f0de1ap-3f, 0x1.f0de1ap-3f));
     p = __ffma2_rn(p, f, make_float2(0x1.62f31ap-1f, 0x1.62f31ap-1f));
     p = __ffma2_rn(p, f, make_float2(0x1.fff692p-1f, 0x1.fff692p-1f));
     float2 r;
-    r.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
-    r.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+    r.x = __uint_as_float(__float_as_uint(t.x) * 0x800000u + __float_as_uint(p.x));     // one IMAD: p * 2^n
+    r.y = __uint_as_float(__float_as_uint(t.y) * 0x800000u + __float_as_uint(p.y));
     return r;
 }
 
@@ -273,7 +282,8 @@ __device__ __forceinline__ float row_max_chunk(const uint32_t (&v)[32], int cbas
     return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// p = 2^(s*c - m) for 32 scores -> 16 packed bf16 pairs; returns the fp32 sum of the 32 probabilities
+// p = 2^(s*c - m) for 32 scores -> 16 packed bf16 pairs; returns the fp32 sum of the 32 probabilities.
+// Of every 4 pairs, UG_ATTN_POLY go through the FMA-pipe polynomial and the rest through MUFU.EX2.
 template <bool kMasked>
 __device__ __forceinline__ float prob_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float m_use, int cbase,
                                             int clo, int chi)
@@ -281,26 +291,19 @@ __device__ __forceinline__ float prob_chunk(const uint32_t (&v)[32], uint32_t (&
     const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_use, -m_use);
     float2 acc0 = make_float2(0.0f, 0.0f), acc1 = make_float2(0.0f, 0.0f);
 #pragma unroll
-    for (int q = 0; q < 32; q += 4) {
-        float2 x0 = __ffma2_rn(make_float2(__uint_as_float(v[q]), __uint_as_float(v[q + 1])), c2, nm2);
-        float2 x1 = __ffma2_rn(make_float2(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3])), c2, nm2);
-        float2 e0 = make_float2(ex2(x0.x), ex2(x0.y));         // MUFU
-#if UG_ATTN_POLY
-        float2 e1 = ex2_poly2(x1);                              // FMA pipe
-#else
-        float2 e1 = make_float2(ex2(x1.x), ex2(x1.y));
-#endif
+    for (int q = 0; q < 32; q += 2) {
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[q]), __uint_as_float(v[q + 1])), c2, nm2);
+        float2 e;
+        if (((q >> 1) & 3) < UG_ATTN_POLY) e = ex2_poly2(x);              // compile-time choice per pair
+        else e = make_float2(ex2(x.x), ex2(x.y));
         if (kMasked) {
             const int col = cbase + q;
-            e0.x = (col >= clo && col < chi) ? e0.x : 0.0f;
-            e0.y = (col + 1 >= clo && col + 1 < chi) ? e0.y : 0.0f;
-            e1.x = (col + 2 >= clo && col + 2 < chi) ? e1.x : 0.0f;
-            e1.y = (col + 3 >= clo && col + 3 < chi) ? e1.y : 0.0f;
+            e.x = (col >= clo && col < chi) ? e.x : 0.0f;
+            e.y = (col + 1 >= clo && col + 1 < chi) ? e.y : 0.0f;
         }
-        pk[q >> 1] = pack_bf16(e0.x, e0.y);
-        pk[(q >> 1) + 1] = pack_bf16(e1.x, e1.y);
-        acc0 = __fadd2_rn(acc0, e0);
-        acc1 = __fadd2_rn(acc1, e1);
+        pk[q >> 1] = pack_bf16(e.x, e.y);
+        if (q & 2) acc1 = __fadd2_rn(acc1, e);
+        else acc0 = __fadd2_rn(acc0, e);
     }
     return (acc0.x + acc0.y) + (acc1.x + acc1.y);
 }
@@ -322,13 +325,7 @@ constexpr uint32_t kOff2V = kOff2K + kKVStages * kTileBytes;
 constexpr uint32_t kOff2Bar = kOff2V + kKVStages * kTileBytes;
 constexpr uint32_t kAttn2Smem = kOff2Bar + 256 + 1024;
 constexpr int kAttn2Threads = 320;           // 2 softmax warpgroups (one per query tile) + TMA warp + MMA warp
-#ifndef UG_ATTN_POLY
-#define UG_ATTN_POLY 0       // 1: every second pair of exponentials on the FMA pipe (polynomial), 0: all on MUFU
-#endif
-#ifndef UG_ATTN_TURNS
-#define UG_ATTN_TURNS 0      // 1: the two softmax warpgroups alternate (named barriers), 0: free running
-#endif
-constexpr float kRescaleTau = 8.0f;          // keep a stale row max until the true max moved by > 2^8 (exact, lazy rescaling)
+constexpr float kStaleSum = 65536.0f;         // a 64-column row sum above this means the softmax reference lags the scores by > ~10 bits
 
 struct Attn2Bars {
     uint64_t q_full;
@@ -374,11 +371,18 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // union [jlo, jhi) of the allowed kv columns over the rows of each tile: a 64-column half outside it is skipped
     const int jloA = (iA < P) ? 0 : P, jhiA = (min(iA + kBM, iEnd) > S) ? L : min(iA + kBM, iEnd);
     const int jloB = (iB < P) ? 0 : P, jhiB = (min(iB + kBM, iEnd) > S) ? L : min(iB + kBM, iEnd);
-    auto half_on = [&](int x, int t, int hf) -> bool {
+    auto half_on_slow = [&](int x, int t, int hf) -> bool {
         const bool tile_on = x == 0 ? (t >= tA0 && t < tA1) : (hasB && t >= tB0 && t < tB1);
         const int c0 = t * kBN + hf * 64;
         return tile_on && c0 < (x == 0 ? jhiA : jhiB) && c0 + 64 > (x == 0 ? jloA : jloB);
     };
+    // bit 2*(t - tU0) + hf of hmask[x]: half (t, hf) of tile x carries work (up to 32 kv tiles = L <= 4096)
+    unsigned long long hmask[2] = {0ull, 0ull};
+    for (int t = tU0; t < tU1; ++t)
+        for (int hf = 0; hf < 2; ++hf)
+            for (int x = 0; x < 2; ++x)
+                if (half_on_slow(x, t, hf)) hmask[x] |= 1ull << (2 * (t - tU0) + hf);
+    auto half_on = [&](int x, int t, int hf) -> bool { return (hmask[x] >> (2 * (t - tU0) + hf)) & 1ull; };
 
     if (tid == 0) {
         bar_init(&bars->q_full, 1);
@@ -471,9 +475,7 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 return s;
             };
             auto last_pv = [&](int x, int t, int hf) {        // is (t, hf) the last half this tile accumulates?
-                for (int hh = hf + 1; hh < 2; ++hh) if (half_on(x, t, hh)) return false;
-                for (int tt = t + 1; tt < tU1; ++tt) for (int hh = 0; hh < 2; ++hh) if (half_on(x, tt, hh)) return false;
-                return true;
+                return (hmask[x] >> (2 * (t - tU0) + hf + 1)) == 0ull;
             };
             bar_wait(&bars->q_full, 0);
             {   // prologue: scores of the first kv tile
@@ -579,60 +581,74 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                         p.dbg[r * 128 + hf * 64 + q] = __uint_as_float(v0[q]);
                         p.dbg[r * 128 + hf * 64 + 32 + q] = __uint_as_float(v1[q]);
                     }
-                float mx = -INFINITY;
-                if (full_tile) {
-                    mx = row_max_chunk<false>(v0, 0, clo, chi, mx);
-                    mx = row_max_chunk<false>(v1, 32, clo, chi, mx);
-                } else {
-                    mx = row_max_chunk<true>(v0, 0, clo, chi, mx);
-                    mx = row_max_chunk<true>(v1, 32, clo, chi, mx);
+                // Optimistic online softmax: the exponentials are taken against the current reference m_ref without
+                // looking for the row max first (any reference is exact as long as O, l and P share it).  The row sum
+                // of the half tells whether the reference went stale (sum > 2^16, inf/NaN, or no reference yet); only
+                // then -- the first half of a row and after rare jumps of the scores -- the true max is computed, O and
+                // l are rescaled and the half is redone.  This removes the max pass and its latency from the hot path.
+                uint32_t pk0[16], pk1[16];
+                float rs = 0.0f, alpha = 1.0f;
+                bool stale = (m_ref == -INFINITY);
+                if (!__any_sync(0xffffffffu, stale)) {
+                    if (full_tile) {
+                        rs = prob_chunk<false>(v0, pk0, c, m_ref, 0, clo, chi) + prob_chunk<false>(v1, pk1, c, m_ref, 32, clo, chi);
+                    } else {
+                        rs = prob_chunk<true>(v0, pk0, c, m_ref, 0, clo, chi) + prob_chunk<true>(v1, pk1, c, m_ref, 32, clo, chi);
+                    }
+                    stale = !(rs <= kStaleSum);
                 }
                 if (r == 0) UG_TL(x, n, 2);
-                // lazy rescaling: keep m_ref while the true max stays within 2^tau of it (exact: O, l and P share m_ref)
-                const float m_true = fmaxf(m_ref, mx * c);
-                const bool move = (m_true - m_ref > kRescaleTau) || (m_ref == -INFINITY && m_true != -INFINITY);
-                const float m_new = move ? m_true : m_ref;
-                const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
-                const float alpha = move ? ex2(m_ref - m_use) : 1.0f;          // 0 when m_ref was -inf
-                // O_x may only be rescaled when no P V of this tile is in flight.  These scores (half number n_pub of
-                // this tile) were issued behind the P V of half n_pub-2, so everything up to n_pub-2 is complete; only the
-                // P V of the half published just before can still be running: wait for its phase of pv_done (the barrier
-                // is at most one phase behind, so the parity wait is exact).  Rare: the max moves by > 2^8 only in the
-                // first tile or two of a row.
-                if (o_live && __any_sync(0xffffffffu, move)) {
-                    bar_wait(&bars->pv_done[x], (uint32_t)(n_pub - 1) & 1u);
-                    tc_fence_after();
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        uint32_t v[32];
-                        tmem_ld32(o_addr + ch * 32, v);
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) * alpha);
-                        tmem_st32(o_addr + ch * 32, v);
+                if (__any_sync(0xffffffffu, stale)) {
+                    float mx = -INFINITY;
+                    if (full_tile) {
+                        mx = row_max_chunk<false>(v0, 0, clo, chi, mx);
+                        mx = row_max_chunk<false>(v1, 32, clo, chi, mx);
+                    } else {
+                        mx = row_max_chunk<true>(v0, 0, clo, chi, mx);
+                        mx = row_max_chunk<true>(v1, 32, clo, chi, mx);
                     }
+                    const float m_true = fmaxf(m_ref, mx * c);
+                    const float m_new = stale ? m_true : m_ref;                  // rows that are fine keep their reference
+                    const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
+                    alpha = (m_new != m_ref) ? ex2(m_ref - m_use) : 1.0f;        // 0 when there was no reference yet
+                    // O_x may only be rescaled when no P V of this tile is in flight.  These scores (half number n_pub
+                    // of this tile) were issued behind the P V of half n_pub-2, so everything up to n_pub-2 is complete;
+                    // only the P V of the half published just before can still be running: wait for its phase of
+                    // pv_done (the barrier is at most one phase behind, so the parity wait is exact).
+                    if (o_live) {
+                        bar_wait(&bars->pv_done[x], (uint32_t)(n_pub - 1) & 1u);
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int ch = 0; ch < 4; ++ch) {
+                            uint32_t v[32];
+                            tmem_ld32(o_addr + ch * 32, v);
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) * alpha);
+                            tmem_st32(o_addr + ch * 32, v);
+                        }
+                    }
+                    if (full_tile) {
+                        rs = prob_chunk<false>(v0, pk0, c, m_use, 0, clo, chi) + prob_chunk<false>(v1, pk1, c, m_use, 32, clo, chi);
+                    } else {
+                        rs = prob_chunk<true>(v0, pk0, c, m_use, 0, clo, chi) + prob_chunk<true>(v1, pk1, c, m_use, 32, clo, chi);
+                    }
+                    m_ref = m_new;
                 }
                 if (r == 0) UG_TL(x, n, 3);
-                // probabilities -> bf16 pairs -> P half in tensor memory (A operand of the second GEMM)
-                float rs = 0.0f;
-                {
-                    uint32_t pk[16];
-#define UG_PROB_CHUNK(vv, ch)                                                                                     \
-    rs += full_tile ? prob_chunk<false>(vv, pk, c, m_use, (ch) * 32, clo, chi)                                    \
-                    : prob_chunk<true>(vv, pk, c, m_use, (ch) * 32, clo, chi);                                    \
-    if (dump && t == t0)                                                                                          \
-        for (int q = 0; q < 16; ++q) {                                                                            \
-            p.dbg[16384 + r * 128 + hf * 64 + (ch) * 32 + 2 * q] = __uint_as_float(pk[q] << 16);                  \
-            p.dbg[16384 + r * 128 + hf * 64 + (ch) * 32 + 2 * q + 1] = __uint_as_float(pk[q] & 0xffff0000u);      \
-        }                                                                                                         \
-    tmem_st16(sh_addr + (ch) * 16, pk);
-                    UG_PROB_CHUNK(v0, 0)
-                    UG_PROB_CHUNK(v1, 1)
-#undef UG_PROB_CHUNK
-                }
+                if (dump && t == t0)
+                    for (int q = 0; q < 16; ++q) {
+                        p.dbg[16384 + r * 128 + hf * 64 + 2 * q] = __uint_as_float(pk0[q] << 16);
+                        p.dbg[16384 + r * 128 + hf * 64 + 2 * q + 1] = __uint_as_float(pk0[q] & 0xffff0000u);
+                        p.dbg[16384 + r * 128 + hf * 64 + 32 + 2 * q] = __uint_as_float(pk1[q] << 16);
+                        p.dbg[16384 + r * 128 + hf * 64 + 32 + 2 * q + 1] = __uint_as_float(pk1[q] & 0xffff0000u);
+                    }
+                // P half -> tensor memory (A operand of the second GEMM), over the score columns already consumed
+                tmem_st16(sh_addr, pk0);
+                tmem_st16(sh_addr + 16, pk1);
+                if (r == 0) UG_TL(x, n, 7);
                 tmem_st_wait();
                 if (r == 0) UG_TL(x, n, 4);
                 l_run = l_run * alpha + rs;
-                m_ref = m_new;
                 o_live = true;
                 ++n_pub;
                 tc_fence_before();

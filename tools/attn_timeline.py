@@ -22,9 +22,9 @@ _lib.lib().ug_debug_set_attn_dump(None)
 t = dump[32768:].cpu().view(4, 64, 8)
 names = {0: "softmaxA", 1: "softmaxB", 2: "mma"}
 for role in (0, 1):
-    print(names[role], "events: wait_start, s_full, pass1_done, rescale_done, pass2_done, arrived")
+    print(names[role], "events: wait_start, s_full, max_done, rescale_done, st_wait_done, arrived, chunk0_done, chunk1_issued")
     for it in range(12):
-        print(it, [int(x) for x in t[role, it, :6].tolist()])
+        print(it, [int(x) for x in t[role, it, :8].tolist()])
 print("mma events per (kv tile, x): wait_start, p_full, pv_issued, qk_issued")
 for it in range(24):
     print(it // 2, "AB"[it % 2], [int(x) for x in t[2, it, :4].tolist()])
