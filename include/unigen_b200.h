@@ -140,13 +140,15 @@ int ug_omni_attention_rows_bf16(const void* q, const void* k, const void* v, voi
  *   ug_add_rmsnorm : x fp32 [M,H] (+= delta bf16 [M,H] if non-NULL, written back); out bf16 [M,H] =
  *                    weight * x * rsqrt(mean(x^2) + eps).  H % 256 == 0, H <= 8192.
  *   ug_rope_qk     : in-place rotate_half RoPE on the q and k heads of qkv bf16 [M,(Hq+2Hkv)*D];
- *                    position = m % L; cos/sin fp32 [L, D/2].
+ *                    position = m % L; cos/sin fp32 [L, D/2].  With kv_cache (bf16 [B, cache_L, 2, Hkv, D]) the rotated
+ *                    k and the v of row m are also written to cache row cache_row_offset + m % L of batch m / L.
  *   ug_swiglu      : act bf16 [M,I] = silu(g) * u, gate_up bf16 [M,2I] = [g | u].
  *   ug_embed_rows  : x fp32 [M,H] = table bf16 [vocab,H][tokens[m]].
  */
 int ug_add_rmsnorm(float* x, const void* delta_bf16, const void* weight_bf16, void* out_bf16,
                    int64_t M, int H, float eps, void* stream);
-int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, int64_t M, int L, int Hq, int Hkv, int D, void* stream);
+int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, int64_t M, int L, int Hq, int Hkv, int D,
+               void* kv_cache_bf16 /* nullable */, int cache_L, int cache_row_offset, void* stream);
 int ug_swiglu(const void* gate_up_bf16, void* act_bf16, int64_t M, int I, void* stream);
 int ug_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64_t M, int H, int64_t vocab, void* stream);
 

@@ -77,7 +77,8 @@ def lib() -> ctypes.CDLL:
     L.ug_add_rmsnorm.restype = c.c_int
     L.ug_add_rmsnorm.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_float, c.c_void_p]
     L.ug_rope_qk.restype = c.c_int
-    L.ug_rope_qk.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p]
+    L.ug_rope_qk.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_int, c.c_int, c.c_int,
+                             c.c_void_p, c.c_int, c.c_int, c.c_void_p]
     L.ug_swiglu.restype = c.c_int
     L.ug_swiglu.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_void_p]
     L.ug_embed_rows.restype = c.c_int

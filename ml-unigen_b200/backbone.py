@@ -137,10 +137,9 @@ class QwenBackboneB200:
         for li, ly in enumerate(self.layers):
             h = ops.add_rmsnorm(x2, ly["ln1"], cfg.rms_norm_eps, delta)
             qkv = F.linear(h, ly["wqkv"], ly["bqkv"])
-            ops.rope_qk_(qkv, cos, sin, L, Hq, Hkv, D)
+            ops.rope_qk_(qkv, cos, sin, L, Hq, Hkv, D, kv_cache=None if kv_cache is None else kv_cache[li])
             q = qkv[:, : Hq * D].view(B, L, Hq, D)
             if kv_cache is not None:
-                kv_cache[li].copy_(qkv[:, Hq * D:].view(B, L, 2, Hkv, D))
                 k, v = kv_cache[li][:, :, 0], kv_cache[li][:, :, 1]
             else:
                 k = qkv[:, Hq * D: (Hq + Hkv) * D].view(B, L, Hkv, D)
@@ -180,9 +179,8 @@ class QwenBackboneB200:
         for li, ly in enumerate(self.layers):
             h = ops.add_rmsnorm(x2, ly["ln1"], cfg.rms_norm_eps, delta)
             qkv = F.linear(h, ly["wqkv"], ly["bqkv"])
-            ops.rope_qk_(qkv, cos, sin, Ls, Hq, Hkv, D)
+            ops.rope_qk_(qkv, cos, sin, Ls, Hq, Hkv, D, kv_cache=kv_cache[li], cache_row_offset=s0)
             q = qkv[:, : Hq * D].view(B, Ls, Hq, D)
-            kv_cache[li][:, s0:].copy_(qkv[:, Hq * D:].view(B, Ls, 2, Hkv, D))
             k, v = kv_cache[li][:, :, 0], kv_cache[li][:, :, 1]
             a = self._attention(q, k, v, pad_len, soi_idx, scale, s0)
             o = F.linear(a.view(M, Hq * D), ly["wo"])

@@ -86,12 +86,15 @@ cudaError_t launch_add_rmsnorm(float* x, const void* delta, const void* w, void*
 
 // ------------------------------------------------------------------------------------------------
 // RoPE (rotate_half convention): out[d] = x[d]*cos[d] - x[d+D/2]*sin[d]; out[d+D/2] = x[d+D/2]*cos[d] + x[d]*sin[d]
-// one thread handles 8 consecutive d of the first half and the matching 8 of the second half of one head
+// one thread handles 8 consecutive d of the first half and the matching 8 of the second half of one head.
+// q heads are rotated in place; k heads are rotated in place and, when a K/V cache is attached, also written to
+// cache[b, row0 + l, 0, hk, :]; v heads are copied to cache[b, row0 + l, 1, hk, :] (fuses the cache update).
 __global__ void __launch_bounds__(256) rope_qk_kernel(uint4* __restrict__ qkv, const float4* __restrict__ cos,
-                                                      const float4* __restrict__ sin, int64_t M, int L, int heads,
-                                                      int D, int row_vecs)
+                                                      const float4* __restrict__ sin, int64_t M, int L, int Hq, int Hkv,
+                                                      int D, int row_vecs, uint4* __restrict__ cache, int cache_L, int row0)
 {
     const int per_head = D / 16;                                   // threads per head
+    const int heads = Hq + Hkv + (cache ? Hkv : 0);                // q, k (rotated) and, with a cache, v (copied)
     const int64_t total = M * heads * per_head;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int t = (int)(idx % per_head);
@@ -100,34 +103,46 @@ __global__ void __launch_bounds__(256) rope_qk_kernel(uint4* __restrict__ qkv, c
         const int pos = (int)(m % L);
         uint4* base = qkv + m * row_vecs + (int64_t)hd * (D / 8);
         uint4 a = base[t], b = base[t + D / 16];
-        const float4* c = cos + ((int64_t)pos * (D / 2) + t * 8) / 4;
-        const float4* s = sin + ((int64_t)pos * (D / 2) + t * 8) / 4;
-        float4 c0 = c[0], c1 = c[1], s0 = s[0], s1 = s[1];
-        float x1[8] = {bf_lo(a.x), bf_hi(a.x), bf_lo(a.y), bf_hi(a.y), bf_lo(a.z), bf_hi(a.z), bf_lo(a.w), bf_hi(a.w)};
-        float x2[8] = {bf_lo(b.x), bf_hi(b.x), bf_lo(b.y), bf_hi(b.y), bf_lo(b.z), bf_hi(b.z), bf_lo(b.w), bf_hi(b.w)};
-        float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        float o1[8], o2[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            o1[k] = x1[k] * cc[k] - x2[k] * sn[k];
-            o2[k] = x2[k] * cc[k] + x1[k] * sn[k];
+        uint4* crow = nullptr;
+        if (cache && hd >= Hq) {
+            const int64_t bb = m / L;
+            const int kvh = hd - Hq;                               // 0..Hkv-1: k heads, Hkv..2Hkv-1: v heads
+            crow = cache + (((bb * cache_L + row0 + pos) * 2 + (kvh >= Hkv ? 1 : 0)) * Hkv + (kvh % Hkv)) * (int64_t)(D / 8);
         }
-        base[t] = make_uint4(pack2(o1[0], o1[1]), pack2(o1[2], o1[3]), pack2(o1[4], o1[5]), pack2(o1[6], o1[7]));
-        base[t + D / 16] = make_uint4(pack2(o2[0], o2[1]), pack2(o2[2], o2[3]), pack2(o2[4], o2[5]), pack2(o2[6], o2[7]));
+        if (hd < Hq + Hkv) {
+            const float4* c = cos + ((int64_t)pos * (D / 2) + t * 8) / 4;
+            const float4* s = sin + ((int64_t)pos * (D / 2) + t * 8) / 4;
+            float4 c0 = c[0], c1 = c[1], s0 = s[0], s1 = s[1];
+            float x1[8] = {bf_lo(a.x), bf_hi(a.x), bf_lo(a.y), bf_hi(a.y), bf_lo(a.z), bf_hi(a.z), bf_lo(a.w), bf_hi(a.w)};
+            float x2[8] = {bf_lo(b.x), bf_hi(b.x), bf_lo(b.y), bf_hi(b.y), bf_lo(b.z), bf_hi(b.z), bf_lo(b.w), bf_hi(b.w)};
+            float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            float o1[8], o2[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                o1[k] = x1[k] * cc[k] - x2[k] * sn[k];
+                o2[k] = x2[k] * cc[k] + x1[k] * sn[k];
+            }
+            a = make_uint4(pack2(o1[0], o1[1]), pack2(o1[2], o1[3]), pack2(o1[4], o1[5]), pack2(o1[6], o1[7]));
+            b = make_uint4(pack2(o2[0], o2[1]), pack2(o2[2], o2[3]), pack2(o2[4], o2[5]), pack2(o2[6], o2[7]));
+            base[t] = a;
+            base[t + D / 16] = b;
+        }
+        if (crow) { crow[t] = a; crow[t + D / 16] = b; }
     }
 }
 
 cudaError_t launch_rope_qk(void* qkv, const float* cos, const float* sin, int64_t M, int L, int Hq, int Hkv, int D,
-                           cudaStream_t stream)
+                           void* kv_cache, int cache_L, int cache_row0, cudaStream_t stream)
 {
     if (D % 16 != 0 || M <= 0 || L <= 0) return cudaErrorInvalidValue;
-    const int heads = Hq + Hkv;                                    // q heads then k heads are contiguous in the fused row
+    const int heads = Hq + Hkv + (kv_cache ? Hkv : 0);             // q heads, k heads, v heads are contiguous in the fused row
     const int row_vecs = (Hq + 2 * Hkv) * D / 8;
     const int64_t total = M * heads * (D / 16);
     unsigned grid = (unsigned)((total + 255) / 256);
     if (grid > 148u * 16u) grid = 148u * 16u;
-    rope_qk_kernel<<<grid, 256, 0, stream>>>((uint4*)qkv, (const float4*)cos, (const float4*)sin, M, L, heads, D, row_vecs);
+    rope_qk_kernel<<<grid, 256, 0, stream>>>((uint4*)qkv, (const float4*)cos, (const float4*)sin, M, L, Hq, Hkv, D, row_vecs,
+                                             (uint4*)kv_cache, cache_L, cache_row0);
     return cudaGetLastError();
 }
 

@@ -12,8 +12,10 @@ cudaError_t launch_add_rmsnorm(float* x, const void* delta_bf16, const void* w_b
 
 // in-place rotary embedding on the q and k heads of a fused qkv activation:
 // qkv bf16 [M, (Hq + 2*Hkv) * D]; position of row m is m % L; cos/sin fp32 [L, D/2].
+// Optional kv_cache bf16 [B, cache_L, 2, Hkv, D]: rotated k and v of row m go to cache row cache_row0 + m % L of
+// batch m / L (fused K/V-cache update of the text-prefix reuse).
 cudaError_t launch_rope_qk(void* qkv_bf16, const float* cos, const float* sin, int64_t M, int L, int Hq, int Hkv, int D,
-                           cudaStream_t stream);
+                           void* kv_cache, int cache_L, int cache_row0, cudaStream_t stream);
 
 // act[M,I] = bf16( silu(g) * u ) with gu bf16 [M, 2*I] = [g | u].  I % 8 == 0.
 cudaError_t launch_swiglu(const void* gu_bf16, void* act_bf16, int64_t M, int I, cudaStream_t stream);

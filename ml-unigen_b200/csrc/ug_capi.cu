@@ -226,12 +226,17 @@ extern "C" int ug_add_rmsnorm(float* x, const void* delta_bf16, const void* weig
     return UG_OK;
 }
 
-extern "C" int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, int64_t M, int L, int Hq, int Hkv, int D, void* stream)
+extern "C" int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, int64_t M, int L, int Hq, int Hkv, int D,
+                          void* kv_cache_bf16, int cache_L, int cache_row_offset, void* stream)
 {
     if (!qkv_bf16 || !cos || !sin) return fail(UG_ERR_NULL, "ug_rope_qk: null pointer");
-    if (M < 1 || L < 1 || D % 16 != 0 || Hq < 1 || Hkv < 1) return fail(UG_ERR_SHAPE, "ug_rope_qk: bad shape");
-    if (!aligned16(qkv_bf16) || !aligned16(cos) || !aligned16(sin)) return fail(UG_ERR_ALIGN, "ug_rope_qk: pointers must be 16-byte aligned");
-    cudaError_t e = ugk::launch_rope_qk(qkv_bf16, cos, sin, M, L, Hq, Hkv, D, static_cast<cudaStream_t>(stream));
+    if (M < 1 || L < 1 || D % 16 != 0 || Hq < 1 || Hkv < 1 || M % L != 0) return fail(UG_ERR_SHAPE, "ug_rope_qk: bad shape");
+    if (kv_cache_bf16 && (cache_row_offset < 0 || cache_row_offset + L > cache_L))
+        return fail(UG_ERR_SHAPE, "ug_rope_qk: cache window [%d, %d) outside cache_L=%d", cache_row_offset, cache_row_offset + L, cache_L);
+    if (!aligned16(qkv_bf16) || !aligned16(cos) || !aligned16(sin) || !aligned16(kv_cache_bf16))
+        return fail(UG_ERR_ALIGN, "ug_rope_qk: pointers must be 16-byte aligned");
+    cudaError_t e = ugk::launch_rope_qk(qkv_bf16, cos, sin, M, L, Hq, Hkv, D, kv_cache_bf16, cache_L, cache_row_offset,
+                                        static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "ug_rope_qk launch");
     return UG_OK;
 }

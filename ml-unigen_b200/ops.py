@@ -152,15 +152,25 @@ def add_rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, delta: Option
     return out
 
 
-def rope_qk_(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, L: int, Hq: int, Hkv: int, D: int) -> torch.Tensor:
-    """In-place RoPE on the q and k heads of the fused qkv activation bf16 [M,(Hq+2Hkv)*D]."""
-    _need_cuda(qkv, cos, sin)
+def rope_qk_(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, L: int, Hq: int, Hkv: int, D: int,
+             kv_cache: Optional[torch.Tensor] = None, cache_row_offset: int = 0) -> torch.Tensor:
+    """In-place RoPE on the q and k heads of the fused qkv activation bf16 [M,(Hq+2Hkv)*D].  With `kv_cache`
+    (bf16 [B, cache_L, 2, Hkv, D]) the rotated k and the v rows are also written into the cache window
+    [cache_row_offset, cache_row_offset + L) -- the K/V-cache update of the text-prefix reuse, fused."""
+    _need_cuda(qkv, cos, sin, kv_cache)
     M = qkv.shape[0]
     if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous() or qkv.shape[1] != (Hq + 2 * Hkv) * D:
         raise ValueError("qkv must be contiguous bf16 [M,(Hq+2Hkv)*D]")
     if cos.dtype != torch.float32 or tuple(cos.shape) != (L, D // 2) or not cos.is_contiguous() or sin.shape != cos.shape:
         raise ValueError("cos/sin must be contiguous fp32 [L, D/2]")
-    _lib.check(_lib.lib().ug_rope_qk(_ptr(qkv), _ptr(cos), _ptr(sin), M, L, Hq, Hkv, D, _stream()))
+    cache_L = 0
+    if kv_cache is not None:
+        if kv_cache.dtype != torch.bfloat16 or not kv_cache.is_contiguous() or tuple(kv_cache.shape[2:]) != (2, Hkv, D) \
+                or kv_cache.shape[0] * L != M:
+            raise ValueError("kv_cache must be contiguous bf16 [M/L, cache_L, 2, Hkv, D]")
+        cache_L = kv_cache.shape[1]
+    _lib.check(_lib.lib().ug_rope_qk(_ptr(qkv), _ptr(cos), _ptr(sin), M, L, Hq, Hkv, D, _ptr(kv_cache), cache_L,
+                                     int(cache_row_offset), _stream()))
     return qkv
 
 

@@ -55,6 +55,15 @@ def test_row_kernels(dev):
     assert (qkv[:, : Hq * D].view(2, L, Hq, D).float() - BO.apply_rope(q0, cos, sin)).abs().max().item() < 4e-2
     assert (qkv[:, Hq * D: (Hq + Hkv) * D].view(2, L, Hkv, D).float() - BO.apply_rope(k0, cos, sin)).abs().max().item() < 4e-2
     assert torch.equal(qkv[:, (Hq + Hkv) * D:], v0)
+    # fused K/V-cache update: rotated k and v land in cache[b, row0 + l]
+    qkv2 = torch.randn(2 * L, (Hq + 2 * Hkv) * D, device=dev, generator=g).bfloat16()
+    ref = qkv2.clone()
+    ops.rope_qk_(ref, cos[:, : D // 2].contiguous(), sin[:, : D // 2].contiguous(), L, Hq, Hkv, D)
+    cache = torch.zeros(2, L + 40, 2, Hkv, D, dtype=torch.bfloat16, device=dev)
+    ops.rope_qk_(qkv2, cos[:, : D // 2].contiguous(), sin[:, : D // 2].contiguous(), L, Hq, Hkv, D, kv_cache=cache, cache_row_offset=40)
+    assert torch.equal(qkv2, ref)
+    assert torch.equal(cache[:, 40:].reshape(2 * L, 2 * Hkv * D), ref[:, Hq * D:])
+    assert int(cache[:, :40].abs().sum()) == 0
     # SwiGLU
     I = 8960
     gu = torch.randn(300, 2 * I, device=dev, generator=g).bfloat16()
