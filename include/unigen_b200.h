@@ -98,8 +98,15 @@ int ug_export_noise(uint64_t philox_seed, uint64_t philox_offset, int64_t batch_
 
 /* test hook: softmax denominators of subsequent decode steps of this thread (float [B,N]; NULL = off) */
 void ug_debug_set_rowsum_out(float* rowsum_out);
-/* test hook: nonzero = evaluate every element of the race exactly (exercises the rare fallback path) */
+/* test hook, bits: 1 = evaluate every element of every row of the race exactly (the e^-16 fallback); 2 = exact
+ * evaluation of the candidate lists on every row; 4 = exact confidence for every token of the mask selection */
 void ug_debug_set_force_full_race(int on);
+/* test hook: 0 = automatic (certified fast kernel when q_noise == NULL, uncond_logits == NULL and V <= 8192),
+ * 1 = always the exact-arithmetic kernel.  Both kernels return the same ids and masks. */
+void ug_debug_set_decode_mode(int mode);
+/* test hook: device uint32[8] counters of the fast kernel's exact paths -- [0] rows whose candidates were evaluated
+ * exactly, [1] rows evaluated exhaustively, [2] mask selections with an undecided band, [3] rows replayed for it, [4..7] reasons of [1] (degenerate row, bound not reached, list A / B overflow) */
+void ug_debug_set_decode_stats(unsigned* counters);
 
 /* ---- omni attention --------------------------------------------------------------------------
  * out = softmax(q k^T * scale + M) v per head, with the omni mask M given in closed form by two

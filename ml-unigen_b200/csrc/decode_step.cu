@@ -28,6 +28,7 @@
 #include <cstdint>
 
 #include "ug_math.cuh"
+#include "ug_ptx.cuh"
 #include "decode_step.h"
 
 namespace ugk {
@@ -37,74 +38,14 @@ constexpr int kThreads = kConsumers + 32;
 constexpr int kVec = 16;
 constexpr int kRowsPerTicket = 2;
 constexpr int kCandMax = 1024;
-constexpr float kRaceT = 16.0f;                 // candidates cover every ratio >= 1/kRaceT
-constexpr float kRaceBound = 1.0f / kRaceT;
-constexpr float kFilterK = 256.0f * kRaceT * 1.0005f;
+constexpr float kRaceBound = 1.0f / 16.0f;      // the candidate lists cover every ratio >= max(best survivor, 1/16)
 
-// ------------------------------------------------------------------------------------------------
-// PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();              // a broken pipeline aborts the launch instead of hanging the GPU
-    }
-}
-// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long best_key(float r, int i)
 {
     return ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);   // r >= 0
 }
-__device__ __forceinline__ float4 ld_stream_f4(const float* p)
-{
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "l"(p));
-    return r;
-}
-
 // ------------------------------------------------------------------------------------------------
 struct Best {
     float r;      // ratio p/q
@@ -116,10 +57,9 @@ __device__ __forceinline__ void best_merge(Best& a, float r, float p, int i)
     if (r > a.r || (r == a.r && i < a.i)) { a.r = r; a.p = p; a.i = i; }
 }
 // exact evaluation of one element of the race (cold path: kept out of line on purpose)
-__device__ __noinline__ void race_eval_exact(float ek, float S, uint32_t coarse, int i, uint64_t rowg, uint64_t seed,
-                                             uint64_t offset, Best& best)
+__device__ __noinline__ void race_eval_exact(float ek, float S, int i, uint64_t rowg, uint64_t seed, uint64_t offset, Best& best)
 {
-    const float q = ug::race_q_from_coarse(coarse, (uint32_t)i, rowg, seed, offset);
+    const float q = ug::race_q((uint32_t)i, rowg, seed, offset);
     const float p = __fdiv_rn(ek, S);
     const float r = __fdiv_rn(p, q);
     best_merge(best, r, p, i);
@@ -140,8 +80,9 @@ struct Ctrl {
     int sel_k;
     int hist[256];
     int wtot[8];
-    uint32_t cand[kCandMax];     // element index | coarse byte << 16
-    float cand_e[kCandMax];
+    uint32_t cand[kCandMax];     // element index
+    uint32_t cand_k[kCandMax];   // its 24-bit noise integer (survivors: from the group call)
+    uint32_t survmask[512];      // bit i: element i is a survivor of the current row (V <= 16384)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -254,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
         c->cand_cnt = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int w = tid; w < 512; w += kThreads) c->survmask[w] = 0u;
     __syncthreads();
 
     if (warp == kConsumers / 32) {
@@ -446,52 +388,64 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
                 }
             }
         } else {
-            // Conservative candidate filter, two elements per step, no branches: an element can reach the
-            // ratio 1/16 only if coarse <= 256*16*p_i.  T = rne(K*e) sits in the low mantissa bits of
-            // fma(K, e, 2^23); with 16-bit fields, (T + 0x8000 - coarse) has bit 15 set iff coarse <= T.
-            const float K = __fdividef(kFilterK, S);
-            const float2 K2 = make_float2(K, K), magic2 = make_float2(8388608.0f, 8388608.0f);
-#pragma unroll
-            for (int ch = 0; ch < kChunks; ++ch) {
-                const int i0 = (ch * kConsumers + tid) * kVec;
-                ug::u32x4 cb = ug::noise_call((uint32_t)(i0 >> 4), ug::kKindCoarse, rowg, a.seed, a.offset);
-                uint32_t cw[4] = {cb.x, cb.y, cb.z, cb.w};
-                uint32_t flags = 0;
-#pragma unroll
-                for (int pr = 0; pr < kVec / 2; ++pr) {
-                    const float2 t2 = __ffma2_rn(K2, make_float2(e[ch * kVec + 2 * pr], e[ch * kVec + 2 * pr + 1]), magic2);
-                    const uint32_t tp = __byte_perm(__float_as_uint(t2.x), __float_as_uint(t2.y), 0x5410);
-                    const uint32_t cp = __byte_perm(cw[pr >> 1], 0u, (pr & 1) ? 0x4342 : 0x4140);   // [c0,0,c1,0]
-                    const uint32_t d = tp + 0x80008000u - cp;
-                    flags = (flags >> 1) | (d & 0x80008000u);
-                }
-                // after kVec/2 = 8 shifts pair p sits at bit 8+p (even element 2p) and bit 24+p (odd element 2p+1)
-                // (rare: ~0.2 candidates per thread)
-                while (flags) {
-                    const int bit = __ffs(flags) - 1;
-                    flags &= flags - 1;
-                    const int k = (bit < 16) ? 2 * (bit - (16 - kVec / 2)) : 2 * (bit - (32 - kVec / 2)) + 1;
+            // Candidates (noise stream v2, ug_math.cuh): (A) the "survivors" of every group of 256 elements (noise
+            // integer < 2^16, q < 2^-8; ~V/256 per row, one Philox call per group) and (B) every other element whose
+            // probability is large enough to reach the best survivor's ratio although its q >= kQFloor.  Both lists are
+            // evaluated with the exact operations, so the filter can never change a result.
+            if (tid < 32 * ((V + 8191) / 8192)) {
+                ug::for_each_survivor((uint32_t)tid, rowg, a.seed, a.offset, [&](uint32_t pos, uint32_t k24) {
+                    const uint32_t i = ug::index_of((uint32_t)tid, pos);
+                    if (i >= (uint32_t)V) return;                  // V = 4096: the second half of the group does not exist
                     const int s = atomicAdd(&c->cand_cnt, 1);
-                    if (s < kCandMax) c->cand[s] = (uint32_t)(i0 + k);
-                }
+                    if (s < kCandMax) { c->cand[s] = i; c->cand_k[s] = k24; }
+                    atomicOr(&c->survmask[i >> 5], 1u << (i & 31u));
+                });
             }
             consumer_bar();                                        // (3)
-            const int cnt = c->cand_cnt;
-            need_full = cnt > kCandMax || a.force_full_race != 0;
-            const int lim = cnt < kCandMax ? cnt : kCandMax;
-            for (int s = tid; s < lim; s += kConsumers) {
+            const int cntA = c->cand_cnt < kCandMax ? c->cand_cnt : kCandMax;
+            auto eval_cand = [&](int s) {
                 const int i = (int)c->cand[s];
                 // the logit is still in the ring slot; e_i is recomputed with the same IEEE operations
                 uint32_t xbits = *reinterpret_cast<const uint16_t*>(srow + 2 * i);
                 if (kCfg) xbits = ug::cfg_mix_bits(xbits, *reinterpret_cast<const uint16_t*>(srow + kRowBytes + 2 * i), a.guidance);
                 const float d = __fadd_rn(__uint_as_float(xbits << 16), -m);
                 const float ei = fast ? ug::expf_fast(d) : ug::expf_exact(d);
-                const ug::u32x4 cb = ug::noise_call((uint32_t)(i >> 4), ug::kKindCoarse, rowg, a.seed, a.offset);
-                const float q = ug::race_q_from_coarse(ug::coarse_byte(cb, (uint32_t)i & 15u), (uint32_t)i, rowg, a.seed, a.offset);
+                const float q = ug::q_from_k24(c->cand_k[s]);
                 const float p = __fdiv_rn(ei, S);
                 const float r = __fdiv_rn(p, q);
                 best_merge(best, r, p, i);
+            };
+            for (int s = tid; s < cntA; s += kConsumers) eval_cand(s);
+            if (best.r >= 0.0f) atomicMax(&c->best, best_key(best.r, best.i));
+            consumer_bar();                                        // (3b)
+            {
+                const float bestA = __uint_as_float((uint32_t)(c->best >> 32));
+                const float R = fmaxf(bestA * (1.0f - 0x1p-12f), kRaceBound);
+                const float thr = R * ug::kQFloor * S * (1.0f - 0x1p-10f);   // e_i < thr  =>  p_i / q_i < R for q_i >= -log(1-2^-8)
+#pragma unroll
+                for (int ch = 0; ch < kChunks; ++ch) {
+                    const int i0 = (ch * kConsumers + tid) * kVec;
+#pragma unroll
+                    for (int k = 0; k < kVec; ++k) {
+                        if (e[ch * kVec + k] >= thr) {
+                            const uint32_t i = (uint32_t)(i0 + k);
+                            if (!((c->survmask[i >> 5] >> (i & 31u)) & 1u)) {
+                                const int s = atomicAdd(&c->cand_cnt, 1);
+                                if (s < kCandMax) c->cand[s] = i;
+                            }
+                        }
+                    }
+                }
             }
+            consumer_bar();                                        // (3c)
+            const int cnt = c->cand_cnt;
+            need_full = cnt > kCandMax || a.force_full_race != 0;
+            const int lim = cnt < kCandMax ? cnt : kCandMax;
+            for (int s = cntA + tid; s < lim; s += kConsumers) {
+                c->cand_k[s] = ug::elem_k24(c->cand[s], rowg, a.seed, a.offset);
+                eval_cand(s);
+            }
+            for (int s = tid; s < cntA; s += kConsumers) c->survmask[c->cand[s] >> 5] = 0u;   // re-arm for the next row
         }
         // ---- block argmax: one 64-bit shared atomicMax per thread that holds a candidate
         unsigned long long mykey = best.r >= 0.0f ? best_key(best.r, best.i) : 0ull;
@@ -506,10 +460,9 @@ __global__ void __launch_bounds__(kThreads, 2) decode_step_kernel(const DecodeAr
 #pragma unroll
             for (int ch = 0; ch < kChunks; ++ch) {
                 const int i0 = (ch * kConsumers + tid) * kVec;
-                ug::u32x4 cb = ug::noise_call((uint32_t)(i0 >> 4), ug::kKindCoarse, rowg, a.seed, a.offset);
-#pragma unroll
+#pragma unroll 1
                 for (int k = 0; k < kVec; ++k)
-                    race_eval_exact(e[ch * kVec + k], S, ug::coarse_byte(cb, k), i0 + k, rowg, a.seed, a.offset, best);
+                    race_eval_exact(e[ch * kVec + k], S, i0 + k, rowg, a.seed, a.offset, best);
             }
             consumer_bar();
             mykey = best_key(best.r, best.i);

@@ -11,6 +11,8 @@
 
 float* ugk_debug_rowsum_out();
 int ugk_debug_force_full_race();
+int ugk_debug_decode_mode();
+unsigned* ugk_debug_decode_stats();
 
 namespace {
 
@@ -62,8 +64,10 @@ size_t ug_decode_step_workspace_bytes(int B, int N, int V)
 {
     (void)V;
     if (B <= 0 || N <= 0) return 0;
-    // [ticket][cta_done] padded to 256 B, then one 64-bit result word per row
-    return 256 + sizeof(unsigned long long) * (size_t)B * N;
+    // [ticket][done] padded to 256 B | one 64-bit result word per row | Gumbel term per token | one flag per 32 tokens
+    const size_t rows = (size_t)B * N;
+    return 256 + sizeof(unsigned long long) * rows + align_up(sizeof(float) * rows, 16) +
+           align_up(sizeof(uint32_t) * (size_t)B * ((N + 31) / 32), 16);
 }
 
 int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float guidance_scale,
@@ -113,8 +117,18 @@ int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float gui
     unsigned* w = static_cast<unsigned*>(workspace);
     a.ticket = w;
     a.cta_done = w + 1;
-    a.slots = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + 256);
-    cudaError_t e = ugk::launch_decode_step(a, sms, static_cast<cudaStream_t>(stream));
+    const size_t rows = (size_t)B * N;
+    char* wsb = static_cast<char*>(workspace);
+    a.slots = reinterpret_cast<unsigned long long*>(wsb + 256);
+    a.gum = reinterpret_cast<float*>(wsb + 256 + sizeof(unsigned long long) * rows);
+    a.gflag = reinterpret_cast<uint32_t*>(wsb + 256 + sizeof(unsigned long long) * rows + align_up(sizeof(float) * rows, 16));
+    a.stats = ugk_debug_decode_stats();
+    // The certified fast kernel (decode_fast.cu) serves the production configuration (in-kernel noise, no CFG,
+    // V <= 8192); injected race noise, CFG and V = 16384 run on the exact-arithmetic kernel (decode_step.cu).
+    // Both produce the ids and masks of the same specification.
+    const bool fast = ugk_debug_decode_mode() == 0 && ugk::decode_fast_supported(a);
+    cudaError_t e = fast ? ugk::launch_decode_fast(a, sms, static_cast<cudaStream_t>(stream))
+                         : ugk::launch_decode_step(a, sms, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "ug_decode_step_bf16 launch");
     return UG_OK;
 }
@@ -210,6 +224,16 @@ float* ugk_debug_rowsum_out() { return g_rowsum_out; }
 static thread_local int g_force_full_race = 0;
 extern "C" void ug_debug_set_force_full_race(int on) { g_force_full_race = on; }
 int ugk_debug_force_full_race() { return g_force_full_race; }
+
+// test hook: 0 = automatic kernel choice (certified fast kernel when eligible), 1 = always the exact-arithmetic kernel
+static thread_local int g_decode_mode = 0;
+extern "C" void ug_debug_set_decode_mode(int mode) { g_decode_mode = mode; }
+int ugk_debug_decode_mode() { return g_decode_mode; }
+
+// test hook: device uint32[4] counters of the fast kernel's exact paths (NULL = off)
+static thread_local unsigned* g_decode_stats = nullptr;
+extern "C" void ug_debug_set_decode_stats(unsigned* p) { g_decode_stats = p; }
+unsigned* ugk_debug_decode_stats() { return g_decode_stats; }
 
 extern "C" void ug_debug_set_attn_dump(float* p) { ugk::set_attn_debug(p); }
 

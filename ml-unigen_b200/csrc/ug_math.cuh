@@ -172,8 +172,33 @@ UG_HD u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1)
     return c;
 }
 
-// counter layout: (block | kind<<28, row, offset_lo, offset_hi ^ row_hi)
-enum : uint32_t { kKindCoarse = 0u, kKindFine = 1u, kKindSelect = 2u };
+// ---------------------------------------------------------------- noise streams
+// counter layout: (block | kind<<28, row, offset_lo, offset_hi ^ row_hi), key = seed
+//
+// Race noise of element i of a row: a 24-bit integer k24, u = (2^24 - k24) * 2^-24 in (0,1], q = -log(u) ~ Exp(1).
+// The top byte of k24 is zero with probability 2^-8 ("survivor": q < 2^-8); only survivors and elements with a
+// large probability can win the race, so the stream is DEFINED such that the survivors of a group of 256 elements
+// come from ONE Philox call (count ~ Binomial(256, 2^-8) by inverse CDF on a 32-bit word, then distinct uniform
+// positions with 16 fine bits each), and the top byte of every other element (uniform on 1..255) and its fine bits
+// come from a per-element word.  The joint law is that of iid uniform 24-bit integers up to the 2^-32 granularity of
+// the inverse CDF.
+enum : uint32_t { kKindGroup = 0u, kKindElem = 1u, kKindSelect = 2u };
+constexpr int kSurvMax = 12;
+// rounded 2^32 * P(Binomial(256, 1/256) >= k), k = 1..12
+#define UG_SURV_T1 2718028156u
+#define UG_SURV_T2 1134904942u
+#define UG_SURV_T3 343343334u
+#define UG_SURV_T4 80524186u
+#define UG_SURV_T5 15334731u
+#define UG_SURV_T6 2450227u
+#define UG_SURV_T7 336494u
+#define UG_SURV_T8 40453u
+#define UG_SURV_T9 4319u
+#define UG_SURV_T10 414u
+#define UG_SURV_T11 36u
+#define UG_SURV_T12 3u
+// q of a non-survivor is >= -log(1 - 2^-8) = 0.0039139...; the filters use this floor (with slack)
+constexpr float kQFloor = 0.0039f;
 
 UG_HD u32x4 noise_call(uint32_t block, uint32_t kind, uint64_t row, uint64_t seed, uint64_t offset)
 {
@@ -190,26 +215,90 @@ UG_HD uint32_t word_of(const u32x4& v, uint32_t i)
     return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }
 
-// exact race noise of element i of row `row`, given its coarse byte
-UG_HD float race_q_from_coarse(uint32_t coarse, uint32_t i, uint64_t row, uint64_t seed, uint64_t offset)
+// element index <-> (group, position): group = the 256 elements of each 8192 that one lane of a warp holds when a
+// row is read with 16-byte loads (lane = (i/8)%32, 32 loads of 8 elements)
+UG_HD uint32_t group_of(uint32_t i) { return ((i >> 3) & 31u) | ((i >> 13) << 5); }
+UG_HD uint32_t pos_of(uint32_t i) { return (((i >> 8) & 31u) << 3) | (i & 7u); }
+UG_HD uint32_t index_of(uint32_t g, uint32_t pos)
 {
-    u32x4 f = noise_call(i >> 3, kKindFine, row, seed, offset);
-    uint32_t fine = (word_of(f, (i & 7u) >> 1) >> (16u * (i & 1u))) & 0xffffu;
-    uint32_t k24 = (coarse << 16) | fine;
+    return ((g >> 5) << 13) | ((pos >> 3) << 8) | ((g & 31u) << 3) | (pos & 7u);
+}
+
+UG_HD int surv_count(uint32_t w0)
+{
+    if (w0 >= UG_SURV_T1) return 0;
+    return 1 + (w0 < UG_SURV_T2) + (w0 < UG_SURV_T3) + (w0 < UG_SURV_T4) + (w0 < UG_SURV_T5) + (w0 < UG_SURV_T6) +
+           (w0 < UG_SURV_T7) + (w0 < UG_SURV_T8) + (w0 < UG_SURV_T9) + (w0 < UG_SURV_T10) + (w0 < UG_SURV_T11) +
+           (w0 < UG_SURV_T12);
+}
+
+// is `pos` among the first nvalid (0..4) bytes of `packed`?
+UG_HD bool ug_has_byte(uint32_t packed, int nvalid, uint32_t pos)
+{
+    return (nvalid > 0 && (packed & 255u) == pos) | (nvalid > 1 && ((packed >> 8) & 255u) == pos) |
+           (nvalid > 2 && ((packed >> 16) & 255u) == pos) | (nvalid > 3 && (packed >> 24) == pos);
+}
+
+// Survivors of group g: calls f(pos, k24) for each (k24 < 2^16).  Words 1.. of the group call (and of follow-up
+// calls block = g | sub<<12) give one candidate each: position = bits 0..7, fine = bits 8..23; a position that was
+// already chosen is skipped.
+template <class F>
+UG_HD void for_each_survivor(uint32_t g, uint64_t row, uint64_t seed, uint64_t offset, F&& f)
+{
+    u32x4 cur = noise_call(g, kKindGroup, row, seed, offset);
+    const int K = surv_count(cur.x);
+    if (K == 0) return;
+    uint32_t pv0 = 0, pv1 = 0, pv2 = 0;                     // chosen positions, one per byte, in order
+    uint32_t widx = 1, sub = 0;
+    int n = 0;
+    while (n < K) {
+        if (widx == 4) { ++sub; cur = noise_call(g | (sub << 12), kKindGroup, row, seed, offset); widx = 0; }
+        const uint32_t w = word_of(cur, widx++);
+        const uint32_t pos = w & 255u;
+        if (ug_has_byte(pv0, n, pos) || (n > 4 && (ug_has_byte(pv1, n - 4, pos) || (n > 8 && ug_has_byte(pv2, n - 8, pos))))) continue;
+        if (n < 4) pv0 |= pos << (8 * n); else if (n < 8) pv1 |= pos << (8 * (n - 4)); else pv2 |= pos << (8 * (n - 8));
+        f(pos, (w >> 8) & 0xffffu);
+        ++n;
+    }
+}
+
+// k24 of an element that is NOT a survivor: top byte uniform on 1..255 (first non-zero byte, most significant
+// first, of word i%4 of the element call; follow-up calls block = i/4 | sub<<16 if all four are zero), fine bits =
+// low 16 bits of the first word.
+UG_HD uint32_t elem_k24(uint32_t i, uint64_t row, uint64_t seed, uint64_t offset)
+{
+    uint32_t w = word_of(noise_call(i >> 2, kKindElem, row, seed, offset), i & 3u);
+    const uint32_t fine = w & 0xffffu;
+    uint32_t top = w >> 24;
+    uint32_t sub = 0;
+    while (top == 0) {
+        ++sub;
+        w = word_of(noise_call((i >> 2) | (sub << 16), kKindElem, row, seed, offset), i & 3u);
+        top = (w >> 24) ? (w >> 24) : (((w >> 16) & 255u) ? ((w >> 16) & 255u) : (((w >> 8) & 255u) ? ((w >> 8) & 255u) : (w & 255u)));
+    }
+    return (top << 16) | fine;
+}
+
+// k24 of any element (generic, slow: one group call + one element call)
+UG_HD uint32_t race_k24(uint32_t i, uint64_t row, uint64_t seed, uint64_t offset)
+{
+    const uint32_t p = pos_of(i);
+    uint32_t found = 0xffffffffu;
+    for_each_survivor(group_of(i), row, seed, offset, [&](uint32_t pos, uint32_t k24) { if (pos == p) found = k24; });
+    if (found != 0xffffffffu) return found;
+    return elem_k24(i, row, seed, offset);
+}
+
+UG_HD float q_from_k24(uint32_t k24)
+{
     uint32_t v = 0x1000000u - k24;
     if (v == 0x1000000u) return 0x1p-25f;
     return -logf_det(UG_MUL((float)v, 0x1p-24f));
 }
 
-UG_HD uint32_t coarse_byte(const u32x4& c, uint32_t k /*0..15*/)
-{
-    return (word_of(c, k >> 2) >> (8u * (k & 3u))) & 0xffu;
-}
-
 UG_HD float race_q(uint32_t i, uint64_t row, uint64_t seed, uint64_t offset)
 {
-    u32x4 c = noise_call(i >> 4, kKindCoarse, row, seed, offset);
-    return race_q_from_coarse(coarse_byte(c, i & 15u), i, row, seed, offset);
+    return q_from_k24(race_k24(i, row, seed, offset));
 }
 
 UG_HD float select_u(uint32_t n, uint64_t batch_row, uint64_t seed, uint64_t offset)

@@ -6,7 +6,7 @@ from ml_unigen_b200 import ops
 dev = torch.device("cuda:0")
 B, N, V = int(os.environ.get("B", 16)), 1024, 8192
 g = torch.Generator(device=dev).manual_seed(0)
-logits = (4.0 * torch.randn(B, N, V, device=dev, generator=g)).bfloat16()
+logits = (float(os.environ.get("SCALE", 4.0)) * torch.randn(B, N, V, device=dev, generator=g)).bfloat16()
 ws = ops.DecodeWorkspace(B, N, V, dev)
 ids0 = torch.full((B, N), 159866, dtype=torch.int64, device=dev)
 for it in range(int(os.environ.get("ITERS", 4))):
