@@ -30,8 +30,6 @@ struct DecodeArgs {
     unsigned long long* slots;   // [B*N] one word per row: (id + 1) << 32 | bits(selected prob); 0 = not published yet
     unsigned* ticket;            // row-pair ticket
     unsigned* cta_done;          // producers finished
-    float* gum;                  // [B*N] Gumbel term of every token (fast kernel; zero at rest)
-    uint32_t* gflag;             // [B*ceil(N/32)] "chunk of 32 Gumbel terms is written" flags (fast kernel; zero at rest)
     unsigned* stats;             // nullable test hook: [0] exact candidate evaluations, [1] exhaustive rows,
                                  // [2] selections with an undecided band, [3] rows replayed exactly for the band, [4..7] reasons of [1]: degenerate row, bound not reached, list A / list B overflow
 };

@@ -64,10 +64,8 @@ size_t ug_decode_step_workspace_bytes(int B, int N, int V)
 {
     (void)V;
     if (B <= 0 || N <= 0) return 0;
-    // [ticket][done] padded to 256 B | one 64-bit result word per row | Gumbel term per token | one flag per 32 tokens
-    const size_t rows = (size_t)B * N;
-    return 256 + sizeof(unsigned long long) * rows + align_up(sizeof(float) * rows, 16) +
-           align_up(sizeof(uint32_t) * (size_t)B * ((N + 31) / 32), 16);
+    // [ticket][done] padded to 256 B | one 64-bit result word per row
+    return 256 + sizeof(unsigned long long) * (size_t)B * N;
 }
 
 int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float guidance_scale,
@@ -117,13 +115,9 @@ int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float gui
     unsigned* w = static_cast<unsigned*>(workspace);
     a.ticket = w;
     a.cta_done = w + 1;
-    const size_t rows = (size_t)B * N;
-    char* wsb = static_cast<char*>(workspace);
-    a.slots = reinterpret_cast<unsigned long long*>(wsb + 256);
-    a.gum = reinterpret_cast<float*>(wsb + 256 + sizeof(unsigned long long) * rows);
-    a.gflag = reinterpret_cast<uint32_t*>(wsb + 256 + sizeof(unsigned long long) * rows + align_up(sizeof(float) * rows, 16));
+    a.slots = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + 256);
     a.stats = ugk_debug_decode_stats();
-    // The certified fast kernel (decode_fast.cu) serves the production configuration (in-kernel noise, no CFG,
+    // The certified fast path (decode_fast.cu: row kernel + selection kernel, two launches on `stream`) serves the production configuration (in-kernel noise, no CFG,
     // V <= 8192); injected race noise, CFG and V = 16384 run on the exact-arithmetic kernel (decode_step.cu).
     // Both produce the ids and masks of the same specification.
     const bool fast = ugk_debug_decode_mode() == 0 && ugk::decode_fast_supported(a);
