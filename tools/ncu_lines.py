@@ -34,7 +34,13 @@ for ln in dis.splitlines():
         line_of[int(m.group(1), 16)] = cur
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
+allrows = list(csv.reader(raw.splitlines()))
+# the report may hold several launches: take the first section whose kernel name contains the plain function name
+plain = re.sub(r"^_ZN\d+\w+?\d+|ILi\d+.*$", "", kern) if kern.startswith("_Z") else re.sub(r"ILi\d+.*$", "", kern)
+starts = [i for i, r in enumerate(allrows) if r and r[0] == "Kernel Name"]
+sel = next((i for i in starts if plain in allrows[i][1]), starts[0])
+end = next((j for j in starts if j > sel), len(allrows))
+rows = allrows[sel:end]
 hdr = rows[1]
 ia, isrc, ismp, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 data = [r for r in rows[2:] if len(r) > iex]
