@@ -46,6 +46,7 @@ def main():
                         flush.zero_()                      # evict the logits from L2 between iterations
                     e0 = torch.cuda.Event(enable_timing=True)
                     e1 = torch.cuda.Event(enable_timing=True)
+                    torch.cuda._sleep(300000)              # keep the GPU busy while the host enqueues: no launch gap inside the events
                     e0.record()
                     ops.decode_step(logits, ids, mask_token_id=MASK_ID, mask_len_cap=cap, temperature=0.5,
                                     workspace=ws, sampled_out=sampled, mask_out=mask, seed=1, offset=it)
