@@ -254,7 +254,7 @@ def run_ours(args):
         dec_avg = sum(dec_ms) / len(dec_ms) * 1e-3
         achieved = flops / attn_avg / 1e12
         attn_share = (sum(attn_ms) + sum(attn_full_ms if attn_full_ms is not attn_ms else [])) * 1e-3 / t_dev
-        launches_per_gen = T * (1 + n_layers * 5 + 1 + 1)
+        launches_per_gen = T * (1 + n_layers * 5 + 1 + 2)     # embed, 5 own kernels per layer, final norm, decode rows + mask selection
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -279,7 +279,7 @@ def run_ours(args):
                                  "text-prefix K/V reuse); the 28 step-0 launches over all L rows are timed separately",
                          "step0_full_avg_launch_ms": (sum(attn_full_ms) / len(attn_full_ms)) if attn_full_ms else None,
                          "step0_full_flops_per_launch": flops_full},
-            "roofline_decode": {"kernel": "decode_step_kernel", "bound": "hbm", "achieved": B * N * V * 2 / dec_avg / 1e9,
+            "roofline_decode": {"kernel": "decode_fast_kernel + select_kernel (the two launches of one decode step)", "bound": "hbm", "achieved": B * N * V * 2 / dec_avg / 1e9,
                                 "peak": peaks["hbm"], "unit": "GB/s", "frac": B * N * V * 2 / dec_avg / 1e9 / peaks["hbm"],
                                 "avg_launch_ms": dec_avg * 1e3, "launches_timed": len(dec_ms),
                                 "note": "average over the 18 mask states of a generation; rows of known tokens are skipped"},

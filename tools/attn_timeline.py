@@ -25,6 +25,6 @@ for role in (0, 1):
     print(names[role], "events: wait_start, s_full, max_done, rescale_done, st_wait_done, arrived, chunk0_done, chunk1_issued")
     for it in range(12):
         print(it, [int(x) for x in t[role, it, :8].tolist()])
-print("mma events per (kv tile, x): wait_start, p_full, pv_issued, qk_issued")
+print("mma (tile A issuer) events per (kv tile, half): wait_start, p_full, pv_issued, qk_issued")
 for it in range(24):
-    print(it // 2, "AB"[it % 2], [int(x) for x in t[2, it, :4].tolist()])
+    print(it // 2, it % 2, [int(x) for x in t[2, it, :4].tolist()])
