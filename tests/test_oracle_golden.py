@@ -108,6 +108,32 @@ def test_philox_noise_statistics():
     assert (u >= 0).all() and (u < 1).all()
 
 
+def test_race_noise_is_iid_exponential():
+    """The race noise is DEFINED through survivor groups (one Philox call per 256 elements) plus per-element words;
+    its law must still be that of iid Exp(1) draws: Kolmogorov-Smirnov on 0.5 M draws, the survivor rate 2^-8, the
+    mean/variance of the per-row survivor count (Binomial(8192, 2^-8)) and the uniformity of the top byte."""
+    from scipy import stats
+    q, _ = O.export_noise(seed=0xC0FFEE, offset=5, B=1, N=64, V=8192, want_u=False)
+    flat = q.reshape(-1).astype(np.float64)
+    assert stats.kstest(flat, "expon").pvalue > 1e-3
+    surv = q < -np.log1p(-2.0 ** -8)                          # k24 < 2^16  <=>  u > 1 - 2^-8
+    n = flat.size
+    rate = surv.mean()
+    assert abs(rate - 2.0 ** -8) < 5 * np.sqrt(2.0 ** -8 / n)
+    per_row = surv.reshape(64, 8192).sum(-1)
+    assert abs(per_row.mean() - 32.0) < 5 * np.sqrt(32.0 / 64) and 10.0 < per_row.var() < 70.0
+    # top byte of k24 = floor(256 * (1 - u)) must be uniform on 0..255
+    top = np.minimum((256.0 * -np.expm1(-flat)).astype(np.int64), 255)
+    counts = np.bincount(top, minlength=256)
+    chi2 = ((counts - n / 256.0) ** 2 / (n / 256.0)).sum()
+    assert chi2 < 400.0                                       # 255 dof: mean 255, sd 22.6
+    # independence of neighbours inside a group and across groups (lag-1 and lag-256 correlations of u)
+    u = np.exp(-flat)
+    for lag in (1, 8, 256):
+        c = np.corrcoef(u[:-lag], u[lag:])[0, 1]
+        assert abs(c) < 5.0 / np.sqrt(n)
+
+
 def test_mask_selection_edge_cases():
     """ties, all-known rows, cap = -1 (last step), N = 2."""
     V = 4096

@@ -3,9 +3,12 @@ Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep "title" > profiles/xy
 import csv, subprocess, sys, collections
 
 rep, title = sys.argv[1], sys.argv[2]
+kfilter = sys.argv[3] if len(sys.argv) > 3 else None          # substring of the kernel name (reports with several launches)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+kcol = hdr.index("Kernel Name")
+vals = next((r for r in rows[2:] if kfilter is None or kfilter in r[kcol]), rows[2])
 want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "launch__waves_per_multiprocessor", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
@@ -30,6 +33,9 @@ for h, v in sorted(st, key=lambda kv: -kv[1])[:10]:
     print(f"| {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} | {v:.3f} |")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 srows = list(csv.reader(src.splitlines()))
+starts = [i for i, r in enumerate(srows) if r and r[0] == "Kernel Name"]
+sel = next((i for i in starts if kfilter is None or kfilter in srows[i][1]), starts[0])
+srows = srows[sel:next((j for j in starts if j > sel), len(srows))]
 h2 = srows[1]
 isrc, iex, ismp = h2.index("Source"), h2.index("Instructions Executed"), h2.index("# Samples")
 data = [r for r in srows[2:] if len(r) > iex]
