@@ -159,6 +159,23 @@ int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, int64_t M, in
 int ug_swiglu(const void* gate_up_bf16, void* act_bf16, int64_t M, int I, void* stream);
 int ug_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64_t M, int H, int64_t vocab, void* stream);
 
+/* ---- linear layers on tcgen05 with fused epilogues -------------------------------
+ * Replaces torch.nn.functional.linear + the elementwise op that follows it in transformers' Qwen2MLP /
+ * Qwen2Attention (models/qwen2/modeling_qwen2.py: `down_proj(act_fn(gate_proj(x)) * up_proj(x))`, q/k/v_proj with
+ * bias), reached from apple/ml-unigen models/unigen.py:260-266.
+ *   a   bf16 [M,K] (row stride lda elements), w bf16 [N,K] (row stride ldw; nn.Linear weight layout), bias bf16 [N] or NULL
+ *   mode UG_GEMM_PLAIN  : out bf16 [M,N]   = a w^T + bias
+ *   mode UG_GEMM_SWIGLU : out bf16 [M,N/2] = silu(g) * u, with g = a Wg^T and u = a Wu^T each rounded to bf16 first (what
+ *                         the unfused autocast path holds) and w = Wg / Wu interleaved in blocks of 128 rows:
+ *                         w[256 j + i] = Wg[128 j + i], w[256 j + 128 + i] = Wu[128 j + i], i < 128 (ug_gemm_pack_gate_up
+ *                         in ml_unigen_b200.ops does this once at load time); bias must be NULL
+ * Supported: N % 256 == 0, K % 64 == 0, strides multiples of 8 elements, 16-byte aligned bases; fp32 accumulation.
+ */
+#define UG_GEMM_PLAIN 0
+#define UG_GEMM_SWIGLU 1
+int ug_gemm_bf16(const void* a, const void* w, const void* bias, void* out, int M, int N, int K,
+                 int64_t lda, int64_t ldw, int64_t ldo, int mode, void* stream);
+
 /* test hook: float[2*128*128 + 2048] receiving the raw scores S and the bf16 probabilities P of the first kv tile
  * of the first query tile of (b=0, h=0), followed by 2048 cycle stamps of CTA (0,0,0) (tools/attn_timeline.py), of
  * subsequent ug_omni_attention_bf16 calls of this thread; NULL = off */

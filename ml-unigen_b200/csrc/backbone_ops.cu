@@ -147,7 +147,9 @@ cudaError_t launch_rope_qk(void* qkv, const float* cos, const float* sin, int64_
 }
 
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
+// MUFU exponential and reciprocal (2 ulp each, far below the bf16 rounding of the result); the fused SwiGLU epilogue of
+// gemm_tc.cu uses the same expression, so the fused and the unfused path agree wherever the GEMM outputs agree
+__device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(g, 1.0f + __expf(-g)) * u; }
 
 __global__ void __launch_bounds__(256) swiglu_kernel(const uint4* __restrict__ gu, uint4* __restrict__ act, int64_t M, int Iv)
 {

@@ -1,0 +1,466 @@
+// gemm_tc.cu -- the linear layers of the Qwen2 backbone (transformers Qwen2Attention / Qwen2MLP, reached from
+// apple/ml-unigen models/unigen.py:260-266) as ONE persistent tcgen05 kernel with the elementwise step that follows
+// the GEMM in the reference fused into its epilogue:
+//   mode plain   : out = x W^T (+ bias)                           q/k/v projection, codebook head
+//   mode SwiGLU  : act = silu(x Wg^T) * (x Wu^T)                  Qwen2MLP.act_fn(gate_proj(x)) * up_proj(x): the
+//                  [M, 2I] gate|up activation (588 MB per layer at config 2) is never written to HBM
+//
+// Shape of the kernel (sm_100a only):
+//   * cluster of 2 CTAs = one SM pair; the pair owns a 256 x 256 output tile; `tcgen05.mma.cta_group::2.kind::f16`
+//     (M=256, N=256, K=16) issued by one thread of the leader CTA; each CTA stages ITS 128 rows of A and ITS half
+//     (128 rows) of the W tile, so every operand byte is read from shared memory by exactly one SM and the per-SM
+//     shared-memory traffic is half of what two independent 128 x 256 tiles would need;
+//   * 6-stage TMA ring (32 KB per stage per CTA, SWIZZLE_128B K-major boxes of 64 k); both CTAs' loads complete on the
+//     LEADER's mbarrier; slots are handed back by a multicast `tcgen05.commit` to both CTAs;
+//   * fp32 accumulators in tensor memory, double buffered (2 x 256 columns): the epilogue of tile i (warps 4-7:
+//     tcgen05.ld -> registers -> swizzled staging tile in shared memory -> TMA store) overlaps the MMAs of tile i+1;
+//   * persistent: cluster c takes tiles c, c+74, ... with the n index fastest, so the 74 tiles in flight share one or
+//     two 256-row panels of A and sweep W, which stays L2 resident (55 MB for gate|up);
+//   * SwiGLU mode: W is stored with gate and up rows interleaved in blocks of 128, so the leader's half of the W tile
+//     is 128 gate rows and the peer's half the matching 128 up rows; accumulator columns [0,128) / [128,256) of one
+//     TMEM lane are gate_j / up_j of the same 128 output features.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "gemm_tc.h"
+
+namespace ugk {
+namespace {
+
+constexpr int kGM = 128;                 // rows of the output tile per CTA (256 per pair)
+constexpr int kGN = 256;                 // columns of the pair's tile = N of one MMA
+constexpr int kGK = 64;                  // k per stage: one 128-byte swizzle row of bf16
+constexpr int kStages = 6;
+constexpr uint32_t kABytes = kGM * kGK * 2;            // 16 KB
+constexpr uint32_t kBBytes = (kGN / 2) * kGK * 2;      // 16 KB: this CTA's half of the W tile
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kOutBytes = 128 * 128 * 2;          // staging tile of the epilogue: [128 rows x 128 bf16], two 64-wide panels
+constexpr uint32_t kOffOut = kStages * kStageBytes;
+constexpr uint32_t kOffBars = kOffOut + kOutBytes;
+constexpr int kThreads = 384;              // warps 0-3: TMA, MMA, TMEM alloc, spare; warps 4-11: epilogue (two per TMEM lane quarter)
+
+struct GemmBars {
+    uint64_t full[kStages];      // leader's: bytes of BOTH CTAs' loads of a stage have landed
+    uint64_t empty[kStages];     // per CTA: the MMAs reading this stage have completed (multicast commit)
+    uint64_t acc_full[2];        // per CTA: accumulator buffer complete (multicast commit)
+    uint64_t acc_empty[2];       // leader's: both CTAs' epilogue warps have drained the buffer (16 arrivals)
+    uint32_t tmem_base;
+};
+constexpr uint32_t kSmemBytes = kOffBars + (uint32_t)sizeof(GemmBars) + 1024;     // + slack for the 1024-byte alignment
+
+struct GemmParams {
+    int M, N, K;
+    int n_mblk, n_nblk, n_kblk;
+    int mode;
+    const __nv_bfloat16* bias;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t n_clusters_x()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(s_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok = 0, spins = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(s_u32(bar)), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();       // a broken pipeline aborts the launch instead of hanging the GPU
+    }
+}
+// TMA tile load of this CTA's box into its own shared memory; the bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// high word of every shared-memory descriptor used here: SBO = 1024 B (8 rows of 128 B), version 1, SWIZZLE_128B
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_kmajor(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+// instruction descriptor: c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+
+// executed by all 32 lanes of the converged MMA warp of the leader CTA; one elected lane issues
+__device__ __forceinline__ void mma_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void commit_pair(uint64_t* bar)
+{
+    asm volatile("{\n\t.reg .pred e;\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(
+                     s_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void pin32(uint32_t (&v)[32])
+{
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// the arithmetic of ug_swiglu (backbone_ops.cu) on the bf16-rounded GEMM outputs, so that the fused and the unfused
+// path differ only by the accumulation order inside the GEMM
+__device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(g, 1.0f + __expf(-g)) * u; }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+               const __grid_constant__ CUtensorMap tm_o, const GemmParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    GemmBars* bars = reinterpret_cast<GemmBars*>(smem + kOffBars);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_tiles = p.n_mblk * p.n_nblk;
+    const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_o) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            bar_init(&bars->full[s], 1);
+            bar_init(&bars->empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            bar_init(&bars->acc_full[i], 1);
+            bar_init(&bars->acc_empty[i], 16);       // 8 epilogue warps x 2 CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {       // all 512 TMEM columns of both SMs of the pair (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&bars->tmem_base)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 0) {
+        // =========================================================== TMA producer (one lane, in both CTAs)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = cid; tile < n_tiles; tile += ncl) {
+                const int mb = tile / p.n_nblk, nb = tile - mb * p.n_nblk;
+                const int m0 = mb * 256 + (int)rank * kGM;
+                const int n0 = nb * kGN + (int)rank * (kGN / 2);
+                for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                    bar_wait(&bars->empty[s], ph ^ 1u);
+                    if (leader) bar_expect_tx(&bars->full[s], 2 * kStageBytes);
+                    const uint32_t fb = mapa(s_u32(&bars->full[s]), 0);
+                    const uint32_t dst = s_u32(smem + s * kStageBytes);
+                    tma_load_2d_pair(dst, &tm_a, fb, kb * kGK, m0);
+                    tma_load_2d_pair(dst + kABytes, &tm_w, fb, kb * kGK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== MMA issuer (leader CTA, whole warp converged)
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc(256, kGN);
+            uint32_t it = 0;
+            int ti = 0;
+            for (int tile = cid; tile < n_tiles; tile += ncl, ++ti) {
+                const uint32_t as = (uint32_t)ti & 1u, aph = ((uint32_t)ti >> 1) & 1u;
+                bar_wait(&bars->acc_empty[as], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d = tmem + as * 256u;
+                for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                    bar_wait(&bars->full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_lo = desc_lo_kmajor(s_u32(smem + s * kStageBytes));
+                    const uint32_t b_lo = desc_lo_kmajor(s_u32(smem + s * kStageBytes + kABytes));
+#pragma unroll
+                    for (int k = 0; k < kGK / 16; ++k)
+                        mma_pair(d, a_lo + 2u * k, b_lo + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    commit_pair(&bars->empty[s]);
+                }
+                commit_pair(&bars->acc_full[as]);
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================================================== epilogue (both CTAs): thread r owns row r of the CTA's 128 rows
+        const int ew = warp & 3;                         // the TMEM lane quarter this warp may read
+        const int cg = (warp - 4) >> 2;                  // which 64 of the 128 staged columns (= which swizzle panel) this warp converts
+        const int r = ew * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(ew * 32) << 16);
+        const uint32_t acc_empty_leader0 = mapa(s_u32(&bars->acc_empty[0]), 0);
+        const uint32_t acc_empty_leader1 = mapa(s_u32(&bars->acc_empty[1]), 0);
+        uint8_t* stg = smem + kOffOut;
+        const uint32_t stg_row = (uint32_t)r * 128u;
+        const uint32_t sw = (uint32_t)(r & 7);
+        const bool issuer = threadIdx.x == 128;
+        int ti = 0;
+        for (int tile = cid; tile < n_tiles; tile += ncl, ++ti) {
+            const int mb = tile / p.n_nblk, nb = tile - mb * p.n_nblk;
+            const int m0 = mb * 256 + (int)rank * kGM;
+            const uint32_t as = (uint32_t)ti & 1u, aph = ((uint32_t)ti >> 1) & 1u;
+            bar_wait(&bars->acc_full[as], aph);
+            tc_fence_after();
+            const uint32_t acc = lane_addr + as * 256u;
+            if (p.mode == kGemmSwiGLU) {
+                if (issuer) bulk_wait_read0();           // the previous tile's TMA store has finished reading the staging tile
+                epi_bar();
+#pragma unroll 1
+                for (int cc = 2 * cg; cc < 2 * cg + 2; ++cc) {
+                    uint32_t g[32], u[32];
+                    tmem_ld32_async(acc + cc * 32, g);
+                    tmem_ld32_async(acc + 128 + cc * 32, u);
+                    tmem_ld_wait();
+                    pin32(g);
+                    pin32(u);
+                    if (cc == 2 * cg + 1) {              // this warp's share of the accumulator buffer is in registers: hand it back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) bar_arrive_cluster(as ? acc_empty_leader1 : acc_empty_leader0);
+                    }
+                    uint32_t o[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float g0 = bf16_round(__uint_as_float(g[2 * q])), g1 = bf16_round(__uint_as_float(g[2 * q + 1]));
+                        const float u0 = bf16_round(__uint_as_float(u[2 * q])), u1 = bf16_round(__uint_as_float(u[2 * q + 1]));
+                        o[q] = pack_bf16(silu_mul(g0, u0), silu_mul(g1, u1));
+                    }
+                    uint8_t* panel = stg + (cc >> 1) * 16384 + stg_row;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t chunk = (uint32_t)((cc & 1) * 4 + j);
+                        *reinterpret_cast<uint4*>(panel + ((chunk ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    }
+                }
+                fence_async_smem();
+                epi_bar();
+                if (issuer && m0 < p.M) {
+                    tma_store_2d(&tm_o, s_u32(stg), nb * 128, m0);
+                    tma_store_2d(&tm_o, s_u32(stg) + 16384, nb * 128 + 64, m0);
+                    bulk_commit();
+                }
+            } else {
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    if (issuer) bulk_wait_read0();
+                    epi_bar();
+#pragma unroll 1
+                    for (int cc = 2 * cg; cc < 2 * cg + 2; ++cc) {
+                        uint32_t v[32];
+                        tmem_ld32_async(acc + half * 128 + cc * 32, v);
+                        tmem_ld_wait();
+                        pin32(v);
+                        if (half == 1 && cc == 2 * cg + 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) bar_arrive_cluster(as ? acc_empty_leader1 : acc_empty_leader0);
+                        }
+                        uint32_t o[16];
+                        if (p.bias) {
+                            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + nb * kGN + half * 128 + cc * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 bv = __ldg(bp + j);
+                                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float b0 = __uint_as_float(bw[e] << 16), b1 = __uint_as_float(bw[e] & 0xffff0000u);
+                                    o[4 * j + e] = pack_bf16(__uint_as_float(v[8 * j + 2 * e]) + b0, __uint_as_float(v[8 * j + 2 * e + 1]) + b1);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) o[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+                        }
+                        uint8_t* panel = stg + (cc >> 1) * 16384 + stg_row;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t chunk = (uint32_t)((cc & 1) * 4 + j);
+                            *reinterpret_cast<uint4*>(panel + ((chunk ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                        }
+                    }
+                    fence_async_smem();
+                    epi_bar();
+                    if (issuer && m0 < p.M) {
+                        tma_store_2d(&tm_o, s_u32(stg), nb * kGN + half * 128, m0);
+                        tma_store_2d(&tm_o, s_u32(stg) + 16384, nb * kGN + half * 128 + 64, m0);
+                        bulk_commit();
+                    }
+                }
+            }
+        }
+        if (issuer) bulk_wait0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();            // the peer may still receive multicast arrivals / remote arrives until both are here
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// row-major bf16 [rows, cols] with row stride ld elements; box = [128 rows x 64 cols], 128-byte swizzle
+bool make_map_2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld)
+{
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* msg, size_t msg_len)
+{
+    if (g.mode != kGemmPlain && g.mode != kGemmSwiGLU) { snprintf(msg, msg_len, "gemm: unsupported mode %d", g.mode); return -4; }
+    if (g.M < 1 || g.N < kGN || g.N % kGN || g.K < kGK || g.K % kGK) {
+        snprintf(msg, msg_len, "gemm: need N %% 256 == 0 and K %% 64 == 0 (M=%d N=%d K=%d)", g.M, g.N, g.K);
+        return -4;
+    }
+    if (g.lda % 8 || g.ldw % 8 || g.ldo % 8) { snprintf(msg, msg_len, "gemm: row strides must be multiples of 8 elements"); return -5; }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { snprintf(msg, msg_len, "cuTensorMapEncodeTiled entry point not available"); return -6; }
+    const int n_out = g.mode == kGemmSwiGLU ? g.N / 2 : g.N;
+    CUtensorMap ta, tw, to;
+    if (!make_map_2d(enc, &ta, g.a, g.M, g.K, g.lda) || !make_map_2d(enc, &tw, g.w, g.N, g.K, g.ldw) ||
+        !make_map_2d(enc, &to, g.out, g.M, n_out, g.ldo)) {
+        snprintf(msg, msg_len, "cuTensorMapEncodeTiled rejected the a/w/out layout");
+        return -3;
+    }
+    GemmParams p;
+    p.M = g.M; p.N = g.N; p.K = g.K;
+    p.n_mblk = (g.M + 255) / 256;
+    p.n_nblk = g.N / kGN;
+    p.n_kblk = g.K / kGK;
+    p.mode = g.mode;
+    p.bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
+    int n_clusters = num_sms / 2;
+    const int n_tiles = p.n_mblk * p.n_nblk;
+    if (n_clusters > n_tiles) n_clusters = n_tiles;
+    if (n_clusters < 1) n_clusters = 1;
+    gemm_tc_kernel<<<dim3(2u * (unsigned)n_clusters), kThreads, kSmemBytes, stream>>>(ta, tw, to, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "gemm launch: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+}  // namespace ugk

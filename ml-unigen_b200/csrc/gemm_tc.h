@@ -1,0 +1,28 @@
+// gemm_tc.h -- bf16 linear layers of the Qwen2 backbone on tcgen05 (2-CTA MMA), with the elementwise step that
+// follows each of them in the reference fused into the epilogue.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ugk {
+
+enum GemmMode : int {
+    kGemmPlain = 0,     // out bf16 [M,N]   = A W^T (+ bias)
+    kGemmSwiGLU = 1,    // out bf16 [M,N/2] = silu(g) * u, W rows interleaved in blocks of 128: [g_0..127 | u_0..127 | g_128.. ]
+    kGemmResidual = 2,  // x fp32 [M,N]    += bf16(A W^T (+ bias))       (residual stream updated in place)
+};
+
+struct GemmArgs {
+    const void* a;      // bf16 [M,K], row stride lda elements
+    const void* w;      // bf16 [N,K], row stride ldw elements
+    const void* bias;   // bf16 [N] or null
+    void* out;          // see GemmMode
+    int64_t lda, ldw, ldo;
+    int M, N, K;
+    int mode;
+};
+
+int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* msg, size_t msg_len);
+
+}  // namespace ugk

@@ -8,6 +8,7 @@
 #include "decode_step.h"
 #include "omni_attention.h"
 #include "backbone_ops.h"
+#include "gemm_tc.h"
 
 float* ugk_debug_rowsum_out();
 int ugk_debug_force_full_race();
@@ -276,5 +277,31 @@ extern "C" int ug_embed_rows(float* x, const void* table_bf16, const int64_t* to
     if (!aligned16(x) || !aligned16(table_bf16)) return fail(UG_ERR_ALIGN, "ug_embed_rows: pointers must be 16-byte aligned");
     cudaError_t e = ugk::launch_embed_rows(x, table_bf16, tokens, M, H, vocab, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "ug_embed_rows launch");
+    return UG_OK;
+}
+
+extern "C" int ug_gemm_bf16(const void* a, const void* w, const void* bias, void* out, int M, int N, int K,
+                            int64_t lda, int64_t ldw, int64_t ldo, int mode, void* stream)
+{
+    if (!a || !w || !out) return fail(UG_ERR_NULL, "ug_gemm_bf16: null pointer");
+    if (mode != UG_GEMM_PLAIN && mode != UG_GEMM_SWIGLU) return fail(UG_ERR_SHAPE, "ug_gemm_bf16: unknown mode %d", mode);
+    if (mode == UG_GEMM_SWIGLU && bias) return fail(UG_ERR_SHAPE, "ug_gemm_bf16: the SwiGLU mode takes no bias");
+    if (M < 1 || N < 256 || N % 256 || K < 64 || K % 64)
+        return fail(UG_ERR_SHAPE, "ug_gemm_bf16: need M >= 1, N %% 256 == 0, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+    const int n_out = mode == UG_GEMM_SWIGLU ? N / 2 : N;
+    if (lda < K || ldw < K || ldo < n_out || lda % 8 || ldw % 8 || ldo % 8)
+        return fail(UG_ERR_SHAPE, "ug_gemm_bf16: row strides must cover the row and be multiples of 8 elements");
+    if (!aligned16(a) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)))
+        return fail(UG_ERR_ALIGN, "ug_gemm_bf16: pointers must be 16-byte aligned");
+    int major = 0;
+    const int sms = sm_count(&major);
+    if (major != 10) return fail(UG_ERR_DEVICE, "ug_gemm_bf16 needs an sm_100 device (tcgen05), found compute capability %d.x", major);
+    ugk::GemmArgs g;
+    g.a = a; g.w = w; g.bias = bias; g.out = out;
+    g.lda = lda; g.ldw = ldw; g.ldo = ldo;
+    g.M = M; g.N = N; g.K = K; g.mode = mode;
+    char msg[256] = "";
+    const int rc = ugk::launch_gemm_tc(g, sms, static_cast<cudaStream_t>(stream), msg, sizeof msg);
+    if (rc != 0) return fail(rc, "ug_gemm_bf16: %s", msg);
     return UG_OK;
 }

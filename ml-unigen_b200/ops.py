@@ -198,3 +198,38 @@ def embed_rows(table: torch.Tensor, tokens: torch.Tensor, out: Optional[torch.Te
         out = torch.empty(M, H, dtype=torch.float32, device=table.device)
     _lib.check(_lib.lib().ug_embed_rows(_ptr(out), _ptr(table), _ptr(tokens), M, H, vocab, _stream()))
     return out
+
+
+GEMM_PLAIN, GEMM_SWIGLU = 0, 1
+
+
+def pack_gate_up(w_gate: torch.Tensor, w_up: torch.Tensor) -> torch.Tensor:
+    """[I,K] gate_proj and up_proj weights -> [2I,K] with rows interleaved in blocks of 128 (the layout
+    `gemm(..., mode=GEMM_SWIGLU)` expects: block 2j = gate rows [128j, 128j+128), block 2j+1 = the same up rows)."""
+    I, K = w_gate.shape
+    if w_up.shape != w_gate.shape or I % 128:
+        raise ValueError("gate/up weights must have the same shape [I,K] with I % 128 == 0")
+    return torch.stack([w_gate.reshape(I // 128, 128, K), w_up.reshape(I // 128, 128, K)], 1).reshape(2 * I, K).contiguous()
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, mode: int = GEMM_PLAIN,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 a [M,K] x w [N,K]^T on the tcgen05 kernel.  mode GEMM_PLAIN: bf16 [M,N] (+bias);
+    GEMM_SWIGLU: w from `pack_gate_up`, returns bf16 [M,N/2] = silu(gate) * up."""
+    _need_cuda(a, w, bias)
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or a.dim() != 2 or w.dim() != 2:
+        raise ValueError("a and w must be 2-D bf16")
+    if a.stride(1) != 1 or w.stride(1) != 1:
+        raise ValueError("a and w must have contiguous rows")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError("inner dimensions differ")
+    n_out = N // 2 if mode == GEMM_SWIGLU else N
+    if out is None:
+        out = torch.empty(M, n_out, dtype=torch.bfloat16, device=a.device)
+    elif out.shape != (M, n_out) or out.dtype != torch.bfloat16 or out.stride(1) != 1:
+        raise ValueError("out must be bf16 [M, n_out] with contiguous rows")
+    _lib.check(_lib.lib().ug_gemm_bf16(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), M, N, K,
+                                       a.stride(0), w.stride(0), out.stride(0), mode, _stream()))
+    return out

@@ -1,0 +1,89 @@
+"""tcgen05 linear-layer kernel (ug_gemm_bf16) against an fp32 torch reference of the same op.
+
+Tolerance (stated, bf16 outputs of an fp32-accumulated product): relative L2 error <= 4e-3 and max-abs error
+<= 2^-6 * max|ref| against the fp32 reference -- one bf16 rounding (2^-9 relative) plus accumulation-order noise;
+cuBLAS' own bf16 output is held to the same bound in the same test."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from ml_unigen_b200 import ops
+    return ops
+
+
+def _check(got, ref32):
+    d = got.float() - ref32
+    rel = (d.norm() / ref32.norm()).item()
+    mx = d.abs().max().item()
+    assert rel <= 4e-3, rel
+    assert mx <= ref32.abs().max().item() * 2 ** -6, mx
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 128), (300, 512, 1536), (1000, 2048, 1536),
+                                   (2082, 1536, 8960), (37, 256, 192)])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_gemm_plain(M, N, K, with_bias):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M * 7 + N + K)
+    x = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, device=dev, generator=g).bfloat16() if with_bias else None
+    got = ops.gemm(x, w, b)
+    ref32 = F.linear(x.float(), w.float(), None if b is None else b.float())
+    _check(got, ref32)
+    _check(F.linear(x, w, b), ref32)
+
+
+def test_gemm_plain_strided_rows():
+    """a and out as column slices of wider tensors (row strides != widths), as the backbone passes them."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    big = torch.randn(515, 2048, device=dev, generator=g).bfloat16()
+    x = big[:, 256:256 + 1536]
+    w = (torch.randn(512, 1536, device=dev, generator=g) * 0.03).bfloat16()
+    out_big = torch.zeros(515, 1024, dtype=torch.bfloat16, device=dev)
+    ops.gemm(x, w, out=out_big[:, 512:])
+    _check(out_big[:, 512:], F.linear(x.float(), w.float()))
+    assert out_big[:, :512].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("M,I,K", [(128, 128, 64), (300, 256, 1536), (2082, 8960, 1536), (16 * 130, 1280, 1536)])
+def test_gemm_swiglu(M, I, K):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + I + K)
+    x = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    wg = (torch.randn(I, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    wu = (torch.randn(I, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    got = ops.gemm(x, ops.pack_gate_up(wg, wu), mode=ops.GEMM_SWIGLU)
+    assert got.shape == (M, I)
+    gate = F.linear(x.float(), wg.float())
+    up = F.linear(x.float(), wu.float())
+    ref32 = F.silu(gate) * up
+    d = got.float() - ref32
+    # two bf16 roundings of the factors plus one of the product
+    assert (d.norm() / ref32.norm()).item() <= 8e-3
+    assert d.abs().max().item() <= ref32.abs().max().item() * 2 ** -5
+    # and against the unfused path (cuBLAS GEMM + ug_swiglu): same arithmetic after the GEMM, so almost every element equal
+    unf = ops.swiglu(F.linear(x, torch.cat([wg, wu], 0)))
+    assert ((got.float() - unf.float()).norm() / unf.float().norm()).item() <= 4e-3
+
+
+def test_gemm_rejects_bad_shapes():
+    ops = _ops()
+    from ml_unigen_b200._lib import UnigenB200Error
+    dev = torch.device("cuda:0")
+    x = torch.zeros(64, 100, dtype=torch.bfloat16, device=dev)
+    w = torch.zeros(256, 100, dtype=torch.bfloat16, device=dev)
+    with pytest.raises((UnigenB200Error, ValueError)):
+        ops.gemm(x, w)
+    x = torch.zeros(64, 128, dtype=torch.bfloat16, device=dev)
+    w = torch.zeros(200, 128, dtype=torch.bfloat16, device=dev)
+    with pytest.raises((UnigenB200Error, ValueError)):
+        ops.gemm(x, w)
