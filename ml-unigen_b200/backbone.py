@@ -12,7 +12,10 @@ laid out for one B200:
 * the LM head is applied only to the N image rows and only to the V codebook rows of the tied
   embedding (models/unigen.py:416 slices exactly that block out of the full-vocabulary logits),
   producing the dense bf16 [B,N,V] tensor the decode-step kernel streams;
-* the dense GEMMs are cuBLAS (torch.nn.functional.linear) in this round.
+* linear layers: gate_proj/up_proj + SwiGLU are ONE launch of the tcgen05 2-CTA kernel
+  (`ops.gemm(..., mode=GEMM_SWIGLU)` on block-interleaved gate|up weights: the [M, 2I] activation never reaches HBM),
+  the codebook head runs on the same kernel; q/k/v, o_proj and down_proj stay on cuBLAS (`F.linear`), which measured
+  4-5 % faster than the own kernel on those three shapes (tools/bench_gemm.py, profiles/r1_gemm_bench.json).
 """
 from __future__ import annotations
 
@@ -65,7 +68,7 @@ class QwenBackboneB200:
                                    weights[p + "self_attn.v_proj.bias"]], 0)),
                 wo=bf(weights[p + "self_attn.o_proj.weight"]),
                 ln2=bf(weights[p + "post_attention_layernorm.weight"]),
-                wgu=bf(torch.cat([weights[p + "mlp.gate_proj.weight"], weights[p + "mlp.up_proj.weight"]], 0)),
+                wgu=ops.pack_gate_up(bf(weights[p + "mlp.gate_proj.weight"]), bf(weights[p + "mlp.up_proj.weight"])),
                 wd=bf(weights[p + "mlp.down_proj.weight"]),
             ))
         self._rope_cache = {}
@@ -147,7 +150,7 @@ class QwenBackboneB200:
             a = self._attention(q, k, v, pad_len, soi_idx, scale, 0)
             o = F.linear(a.view(M, Hq * D), ly["wo"])
             h = ops.add_rmsnorm(x2, ly["ln2"], cfg.rms_norm_eps, o)
-            act = ops.swiglu(F.linear(h, ly["wgu"]))
+            act = ops.gemm(h, ly["wgu"], mode=ops.GEMM_SWIGLU)
             delta = F.linear(act, ly["wd"])
         hn = ops.add_rmsnorm(x2, self.final_norm, cfg.rms_norm_eps, delta).view(B, L, H)
         return hn if rows is None else hn[:, rows]
@@ -185,7 +188,7 @@ class QwenBackboneB200:
             a = self._attention(q, k, v, pad_len, soi_idx, scale, s0)
             o = F.linear(a.view(M, Hq * D), ly["wo"])
             h = ops.add_rmsnorm(x2, ly["ln2"], cfg.rms_norm_eps, o)
-            act = ops.swiglu(F.linear(h, ly["wgu"]))
+            act = ops.gemm(h, ly["wgu"], mode=ops.GEMM_SWIGLU)
             delta = F.linear(act, ly["wd"])
         hn = ops.add_rmsnorm(x2, self.final_norm, cfg.rms_norm_eps, delta).view(B, Ls, H)
         return hn if rows is None else hn[:, rows]
@@ -204,7 +207,9 @@ class QwenBackboneB200:
 
     def codebook_logits(self, hidden_img: torch.Tensor, text_vocab_size: int, V: int) -> torch.Tensor:
         """bf16 [B,N,H] -> bf16 [B,N,V]: tied LM head restricted to rows [text_vocab, text_vocab+V)."""
-        return F.linear(hidden_img, self.embed[text_vocab_size: text_vocab_size + V])
+        B, N, H = hidden_img.shape
+        h2 = hidden_img.reshape(B * N, H)
+        return ops.gemm(h2, self.embed[text_vocab_size: text_vocab_size + V]).view(B, N, V)
 
 
 def _rope_theta(c) -> float:
