@@ -55,7 +55,10 @@ struct GemmParams {
     int M, N, K;
     int n_mblk, n_nblk, n_kblk;
     int mode;
+    int n_rounds, tail_tiles, split_tail;     // see the unit scheduler in the kernel
     const __nv_bfloat16* bias;
+    float* resid;                             // residual mode: fp32 [M, N], row stride ld_resid
+    int64_t ld_resid;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -191,7 +194,7 @@ __device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(
 // ------------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
-               const __grid_constant__ CUtensorMap tm_o, const GemmParams p)
+               const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_o, const GemmParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -199,12 +202,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int n_tiles = p.n_mblk * p.n_nblk;
     const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_wh) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_o) : "memory");
     }
     if (warp == 1 && lane == 0) {
@@ -229,33 +232,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
+    // Work units of this cluster.  Rounds 0 .. n_rounds-1: full 256 x 256 tiles, tile = cid + round * ncl (round robin with
+    // the n index fastest: the tiles in flight share a few 256-row panels of A and sweep W, all L2 resident).  The
+    // remaining R < ncl tiles would leave most SM pairs idle for a whole tile time; when 2R <= ncl they are cut into
+    // 256 x 128 halves (N = 128 MMAs, W boxes of 64 rows per CTA), one half per cluster, and the tail costs half a tile.
+    const int n_units = p.n_rounds + ((p.split_tail ? cid < 2 * p.tail_tiles : cid < p.tail_tiles) ? 1 : 0);
+    auto unit = [&](int i, int& mb, int& nb, int& half) {
+        int tile;
+        if (i < p.n_rounds) {
+            tile = cid + i * ncl;
+            half = -1;
+        } else if (p.split_tail) {
+            tile = p.n_rounds * ncl + (cid >> 1);
+            half = cid & 1;
+        } else {
+            tile = p.n_rounds * ncl + cid;
+            half = -1;
+        }
+        mb = tile / p.n_nblk;
+        nb = tile - mb * p.n_nblk;
+    };
+
     if (warp == 0) {
         // =========================================================== TMA producer (one lane, in both CTAs)
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = cid; tile < n_tiles; tile += ncl) {
-                const int mb = tile / p.n_nblk, nb = tile - mb * p.n_nblk;
+            for (int ui = 0; ui < n_units; ++ui) {
+                int mb, nb, half;
+                unit(ui, mb, nb, half);
                 const int m0 = mb * 256 + (int)rank * kGM;
-                const int n0 = nb * kGN + (int)rank * (kGN / 2);
+                const int n0 = half < 0 ? nb * kGN + (int)rank * (kGN / 2) : nb * kGN + half * 128 + (int)rank * 64;
+                const CUtensorMap* wmap = half < 0 ? &tm_w : &tm_wh;
+                const uint32_t bytes = half < 0 ? 2 * kStageBytes : 2 * (kABytes + kBBytes / 2);
                 for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     bar_wait(&bars->empty[s], ph ^ 1u);
-                    if (leader) bar_expect_tx(&bars->full[s], 2 * kStageBytes);
+                    if (leader) bar_expect_tx(&bars->full[s], bytes);
                     const uint32_t fb = mapa(s_u32(&bars->full[s]), 0);
                     const uint32_t dst = s_u32(smem + s * kStageBytes);
                     tma_load_2d_pair(dst, &tm_a, fb, kb * kGK, m0);
-                    tma_load_2d_pair(dst + kABytes, &tm_w, fb, kb * kGK, n0);
+                    tma_load_2d_pair(dst + kABytes, wmap, fb, kb * kGK, n0);
                 }
             }
         }
     } else if (warp == 1) {
         // =========================================================== MMA issuer (leader CTA, whole warp converged)
         if (leader) {
-            constexpr uint32_t idesc = make_idesc(256, kGN);
             uint32_t it = 0;
-            int ti = 0;
-            for (int tile = cid; tile < n_tiles; tile += ncl, ++ti) {
-                const uint32_t as = (uint32_t)ti & 1u, aph = ((uint32_t)ti >> 1) & 1u;
+            for (int ui = 0; ui < n_units; ++ui) {
+                int mb, nb, half;
+                unit(ui, mb, nb, half);
+                const uint32_t idesc = half < 0 ? make_idesc(256, kGN) : make_idesc(256, kGN / 2);
+                const uint32_t as = (uint32_t)ui & 1u, aph = ((uint32_t)ui >> 1) & 1u;
                 bar_wait(&bars->acc_empty[as], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t d = tmem + as * 256u;
@@ -276,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     } else if (warp >= 4) {
         // =========================================================== epilogue (both CTAs): thread r owns row r of the CTA's 128 rows
         const int ew = warp & 3;                         // the TMEM lane quarter this warp may read
-        const int cg = (warp - 4) >> 2;                  // which 64 of the 128 staged columns (= which swizzle panel) this warp converts
+        const int cg = (warp - 4) >> 2;                  // which 64 of 128 columns (= which swizzle panel of the staging tile) this warp converts
         const int r = ew * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(ew * 32) << 16);
         const uint32_t acc_empty_leader0 = mapa(s_u32(&bars->acc_empty[0]), 0);
@@ -285,16 +313,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const uint32_t stg_row = (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
         const bool issuer = threadIdx.x == 128;
-        int ti = 0;
-        for (int tile = cid; tile < n_tiles; tile += ncl, ++ti) {
-            const int mb = tile / p.n_nblk, nb = tile - mb * p.n_nblk;
+        for (int ui = 0; ui < n_units; ++ui) {
+            int mb, nb, half;
+            unit(ui, mb, nb, half);
             const int m0 = mb * 256 + (int)rank * kGM;
-            const uint32_t as = (uint32_t)ti & 1u, aph = ((uint32_t)ti >> 1) & 1u;
+            const uint32_t as = (uint32_t)ui & 1u, aph = ((uint32_t)ui >> 1) & 1u;
             bar_wait(&bars->acc_full[as], aph);
             tc_fence_after();
             const uint32_t acc = lane_addr + as * 256u;
+            // this warp's share of the accumulator buffer is in registers: hand the buffer back to the MMA warp
+            auto release_acc = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive_cluster(as ? acc_empty_leader1 : acc_empty_leader0);
+            };
             if (p.mode == kGemmSwiGLU) {
-                if (issuer) bulk_wait_read0();           // the previous tile's TMA store has finished reading the staging tile
+                if (issuer) bulk_wait_read0();           // the previous unit's TMA store has finished reading the staging tile
                 epi_bar();
 #pragma unroll 1
                 for (int cc = 2 * cg; cc < 2 * cg + 2; ++cc) {
@@ -304,11 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     tmem_ld_wait();
                     pin32(g);
                     pin32(u);
-                    if (cc == 2 * cg + 1) {              // this warp's share of the accumulator buffer is in registers: hand it back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) bar_arrive_cluster(as ? acc_empty_leader1 : acc_empty_leader0);
-                    }
+                    if (cc == 2 * cg + 1) release_acc();
                     uint32_t o[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
@@ -331,24 +361,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     bulk_commit();
                 }
             } else {
+                const int h0 = half < 0 ? 0 : half, h1 = half < 0 ? 2 : half + 1;
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    if (issuer) bulk_wait_read0();
-                    epi_bar();
+                for (int hh = h0; hh < h1; ++hh) {
+                    const uint32_t acc_h = acc + (half < 0 ? (uint32_t)hh * 128u : 0u);
+                    const int col0 = nb * kGN + hh * 128;             // first output column of this 128-column half
+                    if (p.mode == kGemmPlain) {
+                        if (issuer) bulk_wait_read0();
+                        epi_bar();
+                    }
 #pragma unroll 1
                     for (int cc = 2 * cg; cc < 2 * cg + 2; ++cc) {
                         uint32_t v[32];
-                        tmem_ld32_async(acc + half * 128 + cc * 32, v);
+                        tmem_ld32_async(acc_h + cc * 32, v);
                         tmem_ld_wait();
                         pin32(v);
-                        if (half == 1 && cc == 2 * cg + 1) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) bar_arrive_cluster(as ? acc_empty_leader1 : acc_empty_leader0);
-                        }
+                        if (hh == h1 - 1 && cc == 2 * cg + 1) release_acc();
                         uint32_t o[16];
                         if (p.bias) {
-                            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + nb * kGN + half * 128 + cc * 32);
+                            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0 + cc * 32);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const uint4 bv = __ldg(bp + j);
@@ -363,19 +394,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
                             for (int q = 0; q < 16; ++q) o[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
                         }
-                        uint8_t* panel = stg + (cc >> 1) * 16384 + stg_row;
+                        if (p.mode == kGemmPlain) {
+                            uint8_t* panel = stg + (cc >> 1) * 16384 + stg_row;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t chunk = (uint32_t)((cc & 1) * 4 + j);
-                            *reinterpret_cast<uint4*>(panel + ((chunk ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t chunk = (uint32_t)((cc & 1) * 4 + j);
+                                *reinterpret_cast<uint4*>(panel + ((chunk ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                            }
+                        } else if (m0 + r < p.M) {
+                            // residual mode: x[row, col0 + 32 cc ..] += the bf16-rounded output (what `x += delta` of the
+                            // unfused path adds); each thread owns 128 contiguous bytes of its row
+                            float4* xp = reinterpret_cast<float4*>(p.resid + (int64_t)(m0 + r) * p.ld_resid + col0 + cc * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float4 xv = xp[j];
+                                xv.x += __uint_as_float(o[2 * j] << 16);
+                                xv.y += __uint_as_float(o[2 * j] & 0xffff0000u);
+                                xv.z += __uint_as_float(o[2 * j + 1] << 16);
+                                xv.w += __uint_as_float(o[2 * j + 1] & 0xffff0000u);
+                                xp[j] = xv;
+                            }
                         }
                     }
-                    fence_async_smem();
-                    epi_bar();
-                    if (issuer && m0 < p.M) {
-                        tma_store_2d(&tm_o, s_u32(stg), nb * kGN + half * 128, m0);
-                        tma_store_2d(&tm_o, s_u32(stg) + 16384, nb * kGN + half * 128 + 64, m0);
-                        bulk_commit();
+                    if (p.mode == kGemmPlain) {
+                        fence_async_smem();
+                        epi_bar();
+                        if (issuer && m0 < p.M) {
+                            tma_store_2d(&tm_o, s_u32(stg), col0, m0);
+                            tma_store_2d(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
+                            bulk_commit();
+                        }
                     }
                 }
             }
@@ -409,12 +457,12 @@ EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-// row-major bf16 [rows, cols] with row stride ld elements; box = [128 rows x 64 cols], 128-byte swizzle
-bool make_map_2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld)
+// row-major bf16 [rows, cols] with row stride ld elements; box = [box_rows x 64 cols], 128-byte swizzle
+bool make_map_2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows = 128)
 {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -425,7 +473,7 @@ bool make_map_2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t ro
 
 int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* msg, size_t msg_len)
 {
-    if (g.mode != kGemmPlain && g.mode != kGemmSwiGLU) { snprintf(msg, msg_len, "gemm: unsupported mode %d", g.mode); return -4; }
+    if (g.mode != kGemmPlain && g.mode != kGemmSwiGLU && g.mode != kGemmResidual) { snprintf(msg, msg_len, "gemm: unsupported mode %d", g.mode); return -4; }
     if (g.M < 1 || g.N < kGN || g.N % kGN || g.K < kGK || g.K % kGK) {
         snprintf(msg, msg_len, "gemm: need N %% 256 == 0 and K %% 64 == 0 (M=%d N=%d K=%d)", g.M, g.N, g.K);
         return -4;
@@ -434,9 +482,11 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { snprintf(msg, msg_len, "cuTensorMapEncodeTiled entry point not available"); return -6; }
     const int n_out = g.mode == kGemmSwiGLU ? g.N / 2 : g.N;
-    CUtensorMap ta, tw, to;
+    CUtensorMap ta, tw, twh, to;
+    const bool resid = g.mode == kGemmResidual;        // the fp32 residual stream is updated with plain loads/stores: the out map is unused
     if (!make_map_2d(enc, &ta, g.a, g.M, g.K, g.lda) || !make_map_2d(enc, &tw, g.w, g.N, g.K, g.ldw) ||
-        !make_map_2d(enc, &to, g.out, g.M, n_out, g.ldo)) {
+        !make_map_2d(enc, &twh, g.w, g.N, g.K, g.ldw, 64) ||
+        !make_map_2d(enc, &to, resid ? g.a : g.out, g.M, resid ? g.K : n_out, resid ? g.lda : g.ldo)) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled rejected the a/w/out layout");
         return -3;
     }
@@ -447,17 +497,23 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     p.n_kblk = g.K / kGK;
     p.mode = g.mode;
     p.bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
+    p.resid = resid ? reinterpret_cast<float*>(g.out) : nullptr;
+    p.ld_resid = g.ldo;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    int n_clusters = num_sms / 2;
+    const int max_clusters = num_sms / 2 > 0 ? num_sms / 2 : 1;
     const int n_tiles = p.n_mblk * p.n_nblk;
-    if (n_clusters > n_tiles) n_clusters = n_tiles;
-    if (n_clusters < 1) n_clusters = 1;
-    gemm_tc_kernel<<<dim3(2u * (unsigned)n_clusters), kThreads, kSmemBytes, stream>>>(ta, tw, to, p);
+    const bool can_split = g.mode != kGemmSwiGLU;
+    int n_clusters = max_clusters;
+    if (n_tiles < max_clusters) n_clusters = can_split && 2 * n_tiles <= max_clusters ? 2 * n_tiles : n_tiles;
+    p.n_rounds = n_tiles / n_clusters;
+    p.tail_tiles = n_tiles - p.n_rounds * n_clusters;
+    p.split_tail = can_split && p.tail_tiles > 0 && 2 * p.tail_tiles <= n_clusters ? 1 : 0;
+    gemm_tc_kernel<<<dim3(2u * (unsigned)n_clusters), kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "gemm launch: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;

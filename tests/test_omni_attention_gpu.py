@@ -64,6 +64,9 @@ def _diagnose(q, k, dump, P, S, scale):
     (2, 395, [100, 0], [137, 137]),            # BASELINE config 1 shape (text 128 -> L = 395)
     (3, 300, [0, 130, 299], [10, 140, 299]),   # pads crossing a tile boundary; all-pad-but-one sequence
     (1, 1163, [57], [137]),                    # BASELINE config 2 length
+    (2, 258, [0, 40], [100, 257]),             # L % 256 = 2: GQA-packed tail tile (2 rows x 6 heads in one tile); causal + bidirectional rows in it
+    (2, 533, [3, 0], [200, 520]),              # L % 256 = 21: the largest packed tail (126 rows)
+    (1, 534, [0], [300]),                      # L % 256 = 22: too many rows to pack, ordinary tail tile
 ])
 def test_omni_attention_matches_fp32_reference(dev, B, L, P, S):
     from ml_unigen_b200 import ops, _lib
@@ -145,7 +148,23 @@ def test_query_row_window_equals_full_attention_rows(dev):
     Pt = torch.tensor([0, 57, 99], dtype=torch.int32, device=dev)
     St = torch.full((B,), 137, dtype=torch.int32, device=dev)
     full = ops.omni_attention(q, k, v, Pt, St, D ** -0.5)
-    for s0 in (137, 128, 500):
+    for s0 in (137, 128, 500, 1162, 1150):      # Lq = 1026 / 1035 (packed tails of 2 / 11 rows), 663, 1 and 13 (a packed tile alone)
         part = ops.omni_attention(q[:, s0:], k, v, Pt, St, D ** -0.5, q_offset=s0)
         assert part.shape == (B, L - s0, Hq, D)
         assert torch.equal(part, full[:, s0:]), f"row window s0={s0} differs from the full pass"
+
+
+def test_packed_tail_other_group_sizes(dev):
+    """GQA-packed tail with 2 and 12 query heads per KV head, against the fp32 reference (window pass)."""
+    from ml_unigen_b200 import ops
+    D = 128
+    for Hq, Hkv, L, s0 in ((4, 2, 600, 304), (12, 1, 700, 434), (4, 4, 300, 40)):
+        B = 2
+        q, k, v = _mk(B, L, Hq, Hkv, D, seed=L + Hq, dev=dev)
+        Pt = torch.tensor([0, 33], dtype=torch.int32, device=dev)
+        St = torch.tensor([s0, s0 - 20], dtype=torch.int32, device=dev)
+        ref = BO.attention_ref(q, k, v, Pt, St, D ** -0.5)
+        part = ops.omni_attention(q[:, s0:], k, v, Pt, St, D ** -0.5, q_offset=s0)
+        full = ops.omni_attention(q, k, v, Pt, St, D ** -0.5)
+        assert torch.equal(part, full[:, s0:]), (Hq, Hkv, L, s0)
+        _check(part, ref[:, s0:], tag=f"packed tail Hq={Hq} Hkv={Hkv}")

@@ -42,6 +42,21 @@ def main():
         fl = flops([Pp] * B, [S] * B, L, N)
         row = dict(S=S, N=N, P=Pp, L=L, ms=round(t * 1e3, 4), alg_TFLOPs=round(fl / t / 1e12, 1), dense_TFLOPs=round(4 * B * Hq * L * L * D / t / 1e12, 1),
                    frac_sustained=round(fl / t / 1e12 / pk, 3))
+        # the per-step pass of the text-prefix K/V reuse: only the N+2 image-block query rows (what bench.py runs 17 of 18 steps)
+        qw = q[:, S:]
+        ow = torch.empty_like(qw)
+        for _ in range(3):
+            ops.omni_attention(qw, k, v, P, St, D ** -0.5, out=ow, q_offset=S)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(28):
+            ops.omni_attention(qw, k, v, P, St, D ** -0.5, out=ow, q_offset=S)
+        e1.record()
+        torch.cuda.synchronize()
+        tw = e0.elapsed_time(e1) * 1e-3 / 28
+        flw = 4 * D * Hq * B * (N + 2) * (L - Pp)
+        row["window_ms"] = round(tw * 1e3, 4)
+        row["window_alg_TFLOPs"] = round(flw / tw / 1e12, 1)
         if not os.environ.get("NO_SDPA"):
             mask = BO.omni_additive_mask(P, St, L, torch.bfloat16)
             qq, kk, vv = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3).repeat_interleave(6, 1), v.permute(0, 2, 1, 3).repeat_interleave(6, 1)
