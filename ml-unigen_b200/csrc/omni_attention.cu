@@ -25,6 +25,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 
 #include "omni_attention.h"
 
@@ -185,6 +186,7 @@ struct AttnParams {
     AttnArgs a;
     float scale_log2;       // scale * log2(e)
     int n_qpairs;           // CTAs along the sequence: 256 query rows each
+    int n_split;            // the last n_split pairs of the linear grid are cut into two one-tile CTAs, see the kernel
     int tail_rows;          // > 0: the last pair holds only this many query rows (Lq % 256) and is GQA-packed, see the kernel
     float* dbg;             // optional: dumps S and P of (b=0, h=0, q tile 0, kv tile 0)
 };
@@ -351,8 +353,16 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.a.L;
-    const int qp = p.n_qpairs - 1 - (int)blockIdx.x;        // heaviest (image-row) tiles first
-    const int h = blockIdx.y, b = blockIdx.z;
+    // Linear grid: CTA w < W0 = n_qpairs * Hq * B is the pair (b, h, qp) with the pair index fastest.  The last n_split of
+    // them would start in a final, mostly idle wave (one CTA per SM): each of those pairs is cut in two -- CTA w keeps
+    // tile A and the extra CTA w + n_split takes tile B -- so that the tail of the launch costs one tile, not two.
+    const int W0 = p.n_qpairs * p.a.Hq * p.a.B;
+    int w = (int)blockIdx.x;
+    int only = -1;                                          // -1: both tiles; 0: tile A only; 1: tile B only
+    if (w >= W0) { w -= p.n_split; only = 1; }
+    else if (w >= W0 - p.n_split) only = 0;
+    const int qp = p.n_qpairs - 1 - w % p.n_qpairs;         // heaviest (image-row) tiles first
+    const int h = (w / p.n_qpairs) % p.a.Hq, b = w / (p.n_qpairs * p.a.Hq);
     const int G = p.a.Hq / p.a.Hkv;
     const int hk = h / G;
     // GQA-packed tail: when the last pair holds only R = Lq % 256 rows and R * G <= 128, the R rows of all G query heads
@@ -368,10 +378,15 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
     // the two query tiles of this CTA (local rows lA/lB of q, absolute sequence rows iA/iB) and the kv tiles they need
     const int Lq = p.a.Lq, q0 = p.a.q0;
-    const int lA = qp * 2 * kBM, lB = lA + kBM;
+    const bool pair_has_b = !packed && qp * 2 * kBM + kBM < Lq;
+    if (!pair_has_b) {                                      // nothing to split
+        if (only == 1) return;
+        only = -1;
+    }
+    const int lA = qp * 2 * kBM + (only == 1 ? kBM : 0), lB = lA + kBM;
     const int iA = q0 + lA, iB = q0 + lB;
     const int iEnd = min(q0 + Lq, L);
-    const bool hasB = !packed && lB < Lq;
+    const bool hasB = only < 0 && pair_has_b;
     int tA0, tA1, tB0 = 0, tB1 = 0;
     kv_range(iA, min(iA + R, iEnd), P, S, L, tA0, tA1);
     if (hasB) kv_range(iB, min(iB + kBM, iEnd), P, S, L, tB0, tB1);
@@ -421,7 +436,7 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
     // test hook: cycle stamps of the heaviest CTA (blockIdx 0,0,0) at dbg[32768 + role*512 + iter*8 + event]
-    const bool tl = p.dbg && blockIdx.x == 0 && h == 0 && b == 0;
+    const bool tl = p.dbg && blockIdx.x == 0;
     const uint32_t clk0 = (uint32_t)clock();
 #define UG_TL(role, iter, ev)                                                                            \
     do {                                                                                                 \
@@ -748,7 +763,6 @@ void set_attn_debug(float* p) { g_attn_dbg = p; }
 
 int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, char* msg, size_t msg_len)
 {
-    (void)num_sms;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { snprintf(msg, msg_len, "cuTensorMapEncodeTiled entry point not available"); return -6; }
     CUtensorMap tq, tqt, tk, tv;
@@ -767,6 +781,16 @@ int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, c
     p.scale_log2 = a.scale * 1.4426950408889634f;
     p.n_qpairs = (a.Lq + 2 * kBM - 1) / (2 * kBM);
     p.tail_rows = tail_rows;
+    // CTAs that would start in a last, partly filled wave (one CTA per SM; a tail CTA counts as half a pair)
+    {
+        const int n_full = a.Lq / (2 * kBM) * a.Hq * a.B;
+        const int n_tail = tail ? (tail_rows ? a.Hkv : a.Hq) * a.B : 0;
+        int k = num_sms > 0 ? (n_full + n_tail / 2) % num_sms : 0;
+        if (k > num_sms / 2 || k > n_full) k = 0;
+        static const char* ov = getenv("UG_ATTN_NSPLIT");        // kernel experiments only (tools/bench_attention.py)
+        if (ov && atoi(ov) >= 0 && atoi(ov) <= n_full) k = atoi(ov);
+        p.n_split = k;
+    }
     p.dbg = g_attn_dbg;
     static bool attr_set = false;
     if (!attr_set) {
@@ -774,7 +798,7 @@ int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, c
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    dim3 grid((unsigned)p.n_qpairs, (unsigned)a.Hq, (unsigned)a.B);
+    dim3 grid((unsigned)(p.n_qpairs * a.Hq * a.B + p.n_split));
     omni_attention_kernel<<<grid, kAttn2Threads, kAttn2Smem, stream>>>(tq, tqt, tk, tv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch: %s", cudaGetErrorString(e)); return (int)e; }
