@@ -10,8 +10,9 @@ codebook), random-init weights, bf16, text-to-image, batch 16 per GPU, 1024 imag
 
 Prints ONE JSON line (rank 0).  `value` = images/s with prompts resident in HBM, `e2e` = the same
 through the public API from pinned host memory (H2D of the prompts and D2H of the token grid inside
-the timed region), `roofline` = the dominant hand-written kernel (omni attention, tensor bound) timed
-live with CUDA events inside the timed region, `cpu_baseline` = the oracle port on the host cores.
+the timed region), `roofline` = the dominant kernel of the step (the fused gate|up + SwiGLU tcgen05 GEMM, tensor bound;
+41 % of a layer), `roofline_attention` / `roofline_decode` = the two north-star kernels, all three timed live with
+CUDA events inside the timed region, `cpu_baseline` = the oracle port on the host cores.
 """
 from __future__ import annotations
 
@@ -230,6 +231,7 @@ def run_ours(args):
 
     # timed region 1: prompts resident in HBM; attention and decode launches bracketed by CUDA events
     model.backbone.attn_events = []
+    model.backbone.mlp_events = []
     model.decode_events = []
     sampler = ClockSampler(local) if rank == 0 else None
     t_dev, clocks = timed(args.steps, False, sampler)
@@ -237,7 +239,9 @@ def run_ours(args):
     attn_ms = [t for t, lq in attn_all if lq != L]      # the per-step launches (image-block rows only)
     attn_full_ms = [t for t, lq in attn_all if lq == L] # the step-0 launches over all rows
     dec_ms = [a.elapsed_time(b) for a, b in model.decode_events]
+    mlp_all = [(a.elapsed_time(b), m) for a, b, m in model.backbone.mlp_events]
     model.backbone.attn_events = None
+    model.backbone.mlp_events = None
     model.decode_events = None
     # timed region 2: end to end through the public API from pinned host memory
     t_e2e, _ = timed(args.steps, True)
@@ -254,7 +258,16 @@ def run_ours(args):
         dec_avg = sum(dec_ms) / len(dec_ms) * 1e-3
         achieved = flops / attn_avg / 1e12
         attn_share = (sum(attn_ms) + sum(attn_full_ms if attn_full_ms is not attn_ms else [])) * 1e-3 / t_dev
-        launches_per_gen = T * (1 + n_layers * 5 + 1 + 2)     # embed, 5 own kernels per layer, final norm, decode rows + mask selection
+        # own launches: embed, per layer 2 x add+RMSNorm + RoPE + attention + gate|up GEMM, final norm, head GEMM, decode rows + selection
+        launches_per_gen = T * (1 + n_layers * 5 + 1 + 1 + 2)
+        cfgm = model.backbone.cfg
+        m_step = (e - s) * (N + 2)                           # rows of the per-step passes (text-prefix K/V reuse)
+        mlp_ms = [t for t, m in mlp_all if m == m_step] or [t for t, m in mlp_all]
+        m_rows = m_step if any(m == m_step for _, m in mlp_all) else mlp_all[0][1]
+        mlp_avg = sum(mlp_ms) / len(mlp_ms) * 1e-3
+        mlp_flops = 2.0 * m_rows * 2 * cfgm.intermediate_size * cfgm.hidden_size
+        mlp_tf = mlp_flops / mlp_avg / 1e12
+        mlp_share = sum(t for t, _ in mlp_all) * 1e-3 / t_dev
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -270,8 +283,18 @@ def run_ours(args):
                                    "guidance 0, cosine schedule (BASELINE.json configs[1])",
                        "global_batch": gB, "parallelism": f"replicas x{world}, images sharded, 1 all-gather/generation",
                        "l2": "working set (3.1 GB weights + activations) >> 126 MB L2, no flush needed",
-                       "gemms": "cuBLAS bf16 (torch.nn.functional.linear); attention, decode step and row kernels hand-written"},
-            "roofline": {"kernel": "omni_attention_kernel (tcgen05)", "bound": "tensor", "achieved": achieved,
+                       "gemms": "gate|up + SwiGLU and the codebook head: own tcgen05 2-CTA kernel (ug_gemm_bf16); q/k/v, o, down: cuBLAS bf16 "
+                                "(F.linear); attention, decode step and row kernels hand-written"},
+            "roofline": {"kernel": "gemm_tc_kernel, SwiGLU epilogue (tcgen05 cta_group::2): gate_proj | up_proj + silu(g)*u in one launch",
+                         "bound": "tensor", "achieved": mlp_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                         "frac": mlp_tf / peaks["tf_sust"], "traffic": 618629376,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                         "(profiles/r1_ncu_gemm_swiglu.md); algorithmic bytes 400 MB (A 50 + W 55 + act 294)",
+                         "peak_source": peaks["source"] + " bf16_tflops_sustained (burst: %.1f)" % peaks["tf_burst"],
+                         "flops_per_launch": mlp_flops, "avg_launch_ms": mlp_avg * 1e3, "launches_timed": len(mlp_ms),
+                         "share_of_step": mlp_share,
+                         "note": "2*M*N*K with M = 16 x 1026 rows, N = 17920, K = 1536; launches of MaskGIT steps 1..17"},
+            "roofline_attention": {"kernel": "omni_attention_kernel (tcgen05)", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"], "traffic": None,
                          "peak_source": peaks["source"] + " bf16_tflops_sustained", "flops_per_launch": flops,
                          "avg_launch_ms": attn_avg * 1e3, "launches_timed": len(attn_ms), "share_of_step": attn_share,

@@ -179,6 +179,16 @@ int ug_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64
 int ug_gemm_bf16(const void* a, const void* w, const void* bias, void* out, int M, int N, int K,
                  int64_t lda, int64_t ldw, int64_t ldo, int mode, void* stream);
 
+/* Fused q/k/v projection of Qwen2Attention.forward: qkv bf16 [M,(Hq+2Hkv)*128] = a [w_q|w_k|w_v]^T + bias, then
+ * apply_rotary_pos_emb (rotate_half convention) on the q and k heads in the epilogue of the same launch, and -- with a
+ * K/V cache -- the rotated k row and the v row of sequence row m written to kv_cache[m / L, cache_row_offset + m % L]
+ * (bf16 [B, cache_L, 2, Hkv, 128]).  Replaces ug_gemm_bf16 (plain) + ug_rope_qk; same rounding points: the projection is
+ * rounded to bf16 before the rotation (what the unfused path stores), the rotation is fp32, the result bf16.
+ * Row m is position m % L; cos/sin fp32 [L, 64].  head_dim must be 128. */
+int ug_qkv_rope_bf16(const void* a, const void* w_qkv, const void* bias_qkv, void* qkv_out, int M, int K,
+                     int64_t lda, int64_t ldw, int64_t ldo, const float* cos, const float* sin, int L, int Hq, int Hkv,
+                     void* kv_cache_bf16 /* nullable */, int cache_L, int cache_row_offset, void* stream);
+
 /* test hook: float[2*128*128 + 2048] receiving the raw scores S and the bf16 probabilities P of the first kv tile
  * of the first query tile of (b=0, h=0), followed by 2048 cycle stamps of CTA (0,0,0) (tools/attn_timeline.py), of
  * subsequent ug_omni_attention_bf16 calls of this thread; NULL = off */

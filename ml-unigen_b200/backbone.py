@@ -14,8 +14,9 @@ laid out for one B200:
   producing the dense bf16 [B,N,V] tensor the decode-step kernel streams;
 * linear layers: gate_proj/up_proj + SwiGLU are ONE launch of the tcgen05 2-CTA kernel
   (`ops.gemm(..., mode=GEMM_SWIGLU)` on block-interleaved gate|up weights: the [M, 2I] activation never reaches HBM),
-  the codebook head runs on the same kernel; q/k/v, o_proj and down_proj stay on cuBLAS (`F.linear`), which measured
-  4-5 % faster than the own kernel on those three shapes (tools/bench_gemm.py, profiles/r1_gemm_bench.json).
+  the q/k/v projection + bias + RoPE + K/V-cache update are ONE launch of the same kernel (`ops.qkv_rope`), the codebook
+  head runs on it too; o_proj and down_proj stay on cuBLAS (`F.linear`), which measured 3-4 % faster than the own
+  kernel on those two shapes and has nothing to fuse (tools/bench_gemm.py, profiles/r1_gemm_bench.json).
 """
 from __future__ import annotations
 
@@ -73,6 +74,7 @@ class QwenBackboneB200:
             ))
         self._rope_cache = {}
         self.attn_events = None        # bench hook: list receiving (start, end) CUDA events of every attention launch
+        self.mlp_events = None         # bench hook: the same for every fused gate|up + SwiGLU GEMM launch
 
     # -------------------------------------------------------------------------------------------
     @classmethod
@@ -139,8 +141,8 @@ class QwenBackboneB200:
         delta = None
         for li, ly in enumerate(self.layers):
             h = ops.add_rmsnorm(x2, ly["ln1"], cfg.rms_norm_eps, delta)
-            qkv = F.linear(h, ly["wqkv"], ly["bqkv"])
-            ops.rope_qk_(qkv, cos, sin, L, Hq, Hkv, D, kv_cache=None if kv_cache is None else kv_cache[li])
+            qkv = ops.qkv_rope(h, ly["wqkv"], ly["bqkv"], cos, sin, L, Hq, Hkv,
+                               kv_cache=None if kv_cache is None else kv_cache[li])
             q = qkv[:, : Hq * D].view(B, L, Hq, D)
             if kv_cache is not None:
                 k, v = kv_cache[li][:, :, 0], kv_cache[li][:, :, 1]
@@ -150,7 +152,7 @@ class QwenBackboneB200:
             a = self._attention(q, k, v, pad_len, soi_idx, scale, 0)
             o = F.linear(a.view(M, Hq * D), ly["wo"])
             h = ops.add_rmsnorm(x2, ly["ln2"], cfg.rms_norm_eps, o)
-            act = ops.gemm(h, ly["wgu"], mode=ops.GEMM_SWIGLU)
+            act = self._gate_up(h, ly["wgu"])
             delta = F.linear(act, ly["wd"])
         hn = ops.add_rmsnorm(x2, self.final_norm, cfg.rms_norm_eps, delta).view(B, L, H)
         return hn if rows is None else hn[:, rows]
@@ -177,21 +179,33 @@ class QwenBackboneB200:
         x2 = x.view(M, H)
         cos, sin = self._rope(L)
         cos, sin = cos[s0:], sin[s0:]                       # positions s0 .. L-1 (contiguous row slices)
+        if D != 128:
+            raise ValueError("the fused q/k/v + RoPE kernel needs head_dim 128")
         scale = D ** -0.5
         delta = None
         for li, ly in enumerate(self.layers):
             h = ops.add_rmsnorm(x2, ly["ln1"], cfg.rms_norm_eps, delta)
-            qkv = F.linear(h, ly["wqkv"], ly["bqkv"])
-            ops.rope_qk_(qkv, cos, sin, Ls, Hq, Hkv, D, kv_cache=kv_cache[li], cache_row_offset=s0)
+            qkv = ops.qkv_rope(h, ly["wqkv"], ly["bqkv"], cos, sin, Ls, Hq, Hkv, kv_cache=kv_cache[li], cache_row_offset=s0)
             q = qkv[:, : Hq * D].view(B, Ls, Hq, D)
             k, v = kv_cache[li][:, :, 0], kv_cache[li][:, :, 1]
             a = self._attention(q, k, v, pad_len, soi_idx, scale, s0)
             o = F.linear(a.view(M, Hq * D), ly["wo"])
             h = ops.add_rmsnorm(x2, ly["ln2"], cfg.rms_norm_eps, o)
-            act = ops.gemm(h, ly["wgu"], mode=ops.GEMM_SWIGLU)
+            act = self._gate_up(h, ly["wgu"])
             delta = F.linear(act, ly["wd"])
         hn = ops.add_rmsnorm(x2, self.final_norm, cfg.rms_norm_eps, delta).view(B, Ls, H)
         return hn if rows is None else hn[:, rows]
+
+    def _gate_up(self, h, wgu):
+        ev = self.mlp_events
+        if ev is None:
+            return ops.gemm(h, wgu, mode=ops.GEMM_SWIGLU)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        act = ops.gemm(h, wgu, mode=ops.GEMM_SWIGLU)
+        e1.record()
+        ev.append((e0, e1, h.shape[0]))
+        return act
 
     def _attention(self, q, k, v, pad_len, soi_idx, scale, q_offset):
         ev = self.attn_events

@@ -59,6 +59,11 @@ struct GemmParams {
     const __nv_bfloat16* bias;
     float* resid;                             // residual mode: fp32 [M, N], row stride ld_resid
     int64_t ld_resid;
+    // q/k/v + RoPE mode: row m is position m % rope_L of batch m / rope_L; cos/sin fp32 [rope_L, 64]
+    const float* rope_cos;
+    const float* rope_sin;
+    __nv_bfloat16* kv_cache;                  // nullable: bf16 [B, cache_L, 2, Hkv, 128]
+    int rope_L, rope_Hq, rope_Hkv, cache_L, cache_row0;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,6 +180,21 @@ __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void pin16(uint32_t (&v)[16])
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(v[i]));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void pin32(uint32_t (&v)[32])
 {
@@ -192,6 +212,7 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 __device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(g, 1.0f + __expf(-g)) * u; }
 
 // ------------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_o, const GemmParams p)
@@ -318,6 +339,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             unit(ui, mb, nb, half);
             const int m0 = mb * 256 + (int)rank * kGM;
             const uint32_t as = (uint32_t)ui & 1u, aph = ((uint32_t)ui >> 1) & 1u;
+            // q/k/v + RoPE mode: the cos/sin values of this thread's row and columns (32 cg + [0,32)) are the same for both
+            // heads of the unit; they are requested BEFORE the wait for the accumulator so that their latency is hidden
+            float rope_c[32], rope_s[32];
+            int rope_m = 0, rope_pos = 0;
+            if (MODE == kGemmQkvRope) {
+                rope_m = m0 + r;
+                rope_pos = rope_m % p.rope_L;
+                if ((nb * kGN >> 7) < p.rope_Hq + p.rope_Hkv) {           // at least the first head of the unit is rotated
+                    const float4* cp = reinterpret_cast<const float4*>(p.rope_cos + (int64_t)rope_pos * 64 + cg * 32);
+                    const float4* sp = reinterpret_cast<const float4*>(p.rope_sin + (int64_t)rope_pos * 64 + cg * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 cv = __ldg(cp + j), sv = __ldg(sp + j);
+                        rope_c[4 * j] = cv.x; rope_c[4 * j + 1] = cv.y; rope_c[4 * j + 2] = cv.z; rope_c[4 * j + 3] = cv.w;
+                        rope_s[4 * j] = sv.x; rope_s[4 * j + 1] = sv.y; rope_s[4 * j + 2] = sv.z; rope_s[4 * j + 3] = sv.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { rope_c[j] = 1.0f; rope_s[j] = 0.0f; }
+                }
+            }
             bar_wait(&bars->acc_full[as], aph);
             tc_fence_after();
             const uint32_t acc = lane_addr + as * 256u;
@@ -327,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 __syncwarp();
                 if (lane == 0) bar_arrive_cluster(as ? acc_empty_leader1 : acc_empty_leader0);
             };
-            if (p.mode == kGemmSwiGLU) {
+            if (MODE == kGemmSwiGLU) {
                 if (issuer) bulk_wait_read0();           // the previous unit's TMA store has finished reading the staging tile
                 epi_bar();
 #pragma unroll 1
@@ -360,13 +402,96 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     tma_store_2d(&tm_o, s_u32(stg) + 16384, nb * 128 + 64, m0);
                     bulk_commit();
                 }
+            } else if (MODE == kGemmQkvRope) {
+                // q/k/v projection: every 128-column half is one head.  Thread r holds columns d and d + 64 of its row
+                // (32 + 32 columns per warp group), i.e. both members of each rotate_half pair: bias, bf16 rounding (what
+                // the unfused path stores), rotation by the row's position, bf16 -- then the staging tile / TMA store into
+                // the fused qkv activation and, for k and v heads, the row's bytes straight into the K/V cache.
+                const int h0 = half < 0 ? 0 : half, h1 = half < 0 ? 2 : half + 1;
+#pragma unroll 1
+                for (int hh = h0; hh < h1; ++hh) {
+                    const uint32_t acc_h = acc + (half < 0 ? (uint32_t)hh * 128u : 0u);
+                    const int col0 = nb * kGN + hh * 128;
+                    const int hd = col0 >> 7;                          // head index in [q heads | k heads | v heads]
+                    const bool rot = hd < p.rope_Hq + p.rope_Hkv;
+                    __nv_bfloat16* crow = nullptr;
+                    if (p.kv_cache && hd >= p.rope_Hq && rope_m < p.M) {
+                        const int kvh = hd - p.rope_Hq;                  // [0, Hkv): k heads, [Hkv, 2 Hkv): v heads
+                        const int64_t bb = rope_m / p.rope_L;
+                        crow = p.kv_cache + (((bb * p.cache_L + p.cache_row0 + rope_pos) * 2 + (kvh >= p.rope_Hkv ? 1 : 0)) * p.rope_Hkv +
+                                             kvh % p.rope_Hkv) * 128 + cg * 32;
+                    }
+                    if (issuer) bulk_wait_read0();
+                    epi_bar();
+#pragma unroll
+                    for (int sc = 0; sc < 2; ++sc) {                   // 16 + 16 columns at a time: d = 32 cg + 16 sc + [0,16) and d + 64
+                        uint32_t lo[16], hi[16];
+                        tmem_ld16_async(acc_h + cg * 32 + sc * 16, lo);
+                        tmem_ld16_async(acc_h + 64 + cg * 32 + sc * 16, hi);
+                        tmem_ld_wait();
+                        pin16(lo);
+                        pin16(hi);
+                        if (hh == h1 - 1 && sc == 1) release_acc();
+                        uint32_t o1[8], o2[8];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint4 b1 = make_uint4(0u, 0u, 0u, 0u), b2 = b1;
+                            if (p.bias) {
+                                b1 = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + cg * 32 + sc * 16) + j);
+                                b2 = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + 64 + cg * 32 + sc * 16) + j);
+                            }
+                            const uint32_t bw1[4] = {b1.x, b1.y, b1.z, b1.w}, bw2[4] = {b2.x, b2.y, b2.z, b2.w};
+                            float x1[8], x2[8];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                x1[2 * e] = bf16_round(__uint_as_float(lo[8 * j + 2 * e]) + __uint_as_float(bw1[e] << 16));
+                                x1[2 * e + 1] = bf16_round(__uint_as_float(lo[8 * j + 2 * e + 1]) + __uint_as_float(bw1[e] & 0xffff0000u));
+                                x2[2 * e] = bf16_round(__uint_as_float(hi[8 * j + 2 * e]) + __uint_as_float(bw2[e] << 16));
+                                x2[2 * e + 1] = bf16_round(__uint_as_float(hi[8 * j + 2 * e + 1]) + __uint_as_float(bw2[e] & 0xffff0000u));
+                            }
+                            if (rot) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float a = x1[e], b = x2[e];
+                                    const float cs = rope_c[16 * sc + 8 * j + e], sn = rope_s[16 * sc + 8 * j + e];
+                                    x1[e] = a * cs - b * sn;
+                                    x2[e] = b * cs + a * sn;
+                                }
+                            }
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                o1[4 * j + e] = pack_bf16(x1[2 * e], x1[2 * e + 1]);
+                                o2[4 * j + e] = pack_bf16(x2[2 * e], x2[2 * e + 1]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint32_t chunk = (uint32_t)(cg * 4 + sc * 2 + j);
+                            const uint4 v1 = make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+                            const uint4 v2 = make_uint4(o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
+                            *reinterpret_cast<uint4*>(stg + stg_row + ((chunk ^ sw) << 4)) = v1;
+                            *reinterpret_cast<uint4*>(stg + 16384 + stg_row + ((chunk ^ sw) << 4)) = v2;
+                            if (crow) {
+                                *reinterpret_cast<uint4*>(crow + sc * 16 + 8 * j) = v1;
+                                *reinterpret_cast<uint4*>(crow + 64 + sc * 16 + 8 * j) = v2;
+                            }
+                        }
+                    }
+                    fence_async_smem();
+                    epi_bar();
+                    if (issuer && m0 < p.M) {
+                        tma_store_2d(&tm_o, s_u32(stg), col0, m0);
+                        tma_store_2d(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
+                        bulk_commit();
+                    }
+                }
             } else {
                 const int h0 = half < 0 ? 0 : half, h1 = half < 0 ? 2 : half + 1;
 #pragma unroll 1
                 for (int hh = h0; hh < h1; ++hh) {
                     const uint32_t acc_h = acc + (half < 0 ? (uint32_t)hh * 128u : 0u);
                     const int col0 = nb * kGN + hh * 128;             // first output column of this 128-column half
-                    if (p.mode == kGemmPlain) {
+                    if (MODE == kGemmPlain) {
                         if (issuer) bulk_wait_read0();
                         epi_bar();
                     }
@@ -394,7 +519,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
                             for (int q = 0; q < 16; ++q) o[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
                         }
-                        if (p.mode == kGemmPlain) {
+                        if (MODE == kGemmPlain) {
                             uint8_t* panel = stg + (cc >> 1) * 16384 + stg_row;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -416,7 +541,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             }
                         }
                     }
-                    if (p.mode == kGemmPlain) {
+                    if (MODE == kGemmPlain) {
                         fence_async_smem();
                         epi_bar();
                         if (issuer && m0 < p.M) {
@@ -473,7 +598,7 @@ bool make_map_2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t ro
 
 int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* msg, size_t msg_len)
 {
-    if (g.mode != kGemmPlain && g.mode != kGemmSwiGLU && g.mode != kGemmResidual) { snprintf(msg, msg_len, "gemm: unsupported mode %d", g.mode); return -4; }
+    if (g.mode != kGemmPlain && g.mode != kGemmSwiGLU && g.mode != kGemmResidual && g.mode != kGemmQkvRope) { snprintf(msg, msg_len, "gemm: unsupported mode %d", g.mode); return -4; }
     if (g.M < 1 || g.N < kGN || g.N % kGN || g.K < kGK || g.K % kGK) {
         snprintf(msg, msg_len, "gemm: need N %% 256 == 0 and K %% 64 == 0 (M=%d N=%d K=%d)", g.M, g.N, g.K);
         return -4;
@@ -499,9 +624,19 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     p.bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
     p.resid = resid ? reinterpret_cast<float*>(g.out) : nullptr;
     p.ld_resid = g.ldo;
+    p.rope_cos = g.rope_cos; p.rope_sin = g.rope_sin;
+    p.kv_cache = reinterpret_cast<__nv_bfloat16*>(g.kv_cache);
+    p.rope_L = g.rope_L; p.rope_Hq = g.rope_Hq; p.rope_Hkv = g.rope_Hkv; p.cache_L = g.cache_L; p.cache_row0 = g.cache_row0;
+    if (g.mode == kGemmQkvRope && (!g.rope_cos || !g.rope_sin || g.rope_L < 1 || g.N != (g.rope_Hq + 2 * g.rope_Hkv) * 128)) {
+        snprintf(msg, msg_len, "gemm: q/k/v + RoPE mode needs cos/sin tables, rope_L >= 1 and N == (Hq + 2 Hkv) * 128");
+        return -4;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmSwiGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmResidual>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmQkvRope>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
@@ -513,7 +648,13 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     p.n_rounds = n_tiles / n_clusters;
     p.tail_tiles = n_tiles - p.n_rounds * n_clusters;
     p.split_tail = can_split && p.tail_tiles > 0 && 2 * p.tail_tiles <= n_clusters ? 1 : 0;
-    gemm_tc_kernel<<<dim3(2u * (unsigned)n_clusters), kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p);
+    const dim3 grid(2u * (unsigned)n_clusters);
+    switch (g.mode) {
+        case kGemmPlain: gemm_tc_kernel<kGemmPlain><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
+        case kGemmSwiGLU: gemm_tc_kernel<kGemmSwiGLU><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
+        case kGemmResidual: gemm_tc_kernel<kGemmResidual><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
+        default: gemm_tc_kernel<kGemmQkvRope><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "gemm launch: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;

@@ -11,6 +11,8 @@ enum GemmMode : int {
     kGemmPlain = 0,     // out bf16 [M,N]   = A W^T (+ bias)
     kGemmSwiGLU = 1,    // out bf16 [M,N/2] = silu(g) * u, W rows interleaved in blocks of 128: [g_0..127 | u_0..127 | g_128.. ]
     kGemmResidual = 2,  // x fp32 [M,N]    += bf16(A W^T (+ bias))       (residual stream updated in place)
+    kGemmQkvRope = 3,   // out bf16 [M,N]   = rope(A W^T + bias) on the q and k heads (head_dim 128), v heads copied; k/v rows also
+                        // written to the K/V cache
 };
 
 struct GemmArgs {
@@ -21,6 +23,11 @@ struct GemmArgs {
     int64_t lda, ldw, ldo;
     int M, N, K;
     int mode;
+    // kGemmQkvRope only
+    const float* rope_cos = nullptr;   // fp32 [rope_L, 64]
+    const float* rope_sin = nullptr;
+    void* kv_cache = nullptr;          // nullable: bf16 [B, cache_L, 2, Hkv, 128]
+    int rope_L = 0, rope_Hq = 0, rope_Hkv = 0, cache_L = 0, cache_row0 = 0;
 };
 
 int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* msg, size_t msg_len);

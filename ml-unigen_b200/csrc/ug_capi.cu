@@ -305,3 +305,33 @@ extern "C" int ug_gemm_bf16(const void* a, const void* w, const void* bias, void
     if (rc != 0) return fail(rc, "ug_gemm_bf16: %s", msg);
     return UG_OK;
 }
+
+extern "C" int ug_qkv_rope_bf16(const void* a, const void* w_qkv, const void* bias_qkv, void* qkv_out, int M, int K,
+                                int64_t lda, int64_t ldw, int64_t ldo, const float* cos, const float* sin, int L, int Hq, int Hkv,
+                                void* kv_cache_bf16, int cache_L, int cache_row_offset, void* stream)
+{
+    if (!a || !w_qkv || !qkv_out || !cos || !sin) return fail(UG_ERR_NULL, "ug_qkv_rope_bf16: null pointer");
+    if (Hq < 1 || Hkv < 1 || L < 1 || M < 1) return fail(UG_ERR_SHAPE, "ug_qkv_rope_bf16: bad shape");
+    const int N = (Hq + 2 * Hkv) * 128;
+    if (N % 256 || K < 64 || K % 64) return fail(UG_ERR_SHAPE, "ug_qkv_rope_bf16: need (Hq + 2 Hkv) even and K %% 64 == 0 (N=%d K=%d)", N, K);
+    if (lda < K || ldw < K || ldo < N || lda % 8 || ldw % 8 || ldo % 8)
+        return fail(UG_ERR_SHAPE, "ug_qkv_rope_bf16: row strides must cover the row and be multiples of 8 elements");
+    if (!aligned16(a) || !aligned16(w_qkv) || !aligned16(qkv_out) || (bias_qkv && !aligned16(bias_qkv)) || !aligned16(cos) ||
+        !aligned16(sin) || (kv_cache_bf16 && !aligned16(kv_cache_bf16)))
+        return fail(UG_ERR_ALIGN, "ug_qkv_rope_bf16: pointers must be 16-byte aligned");
+    if (kv_cache_bf16 && (cache_row_offset < 0 || cache_row_offset + L > cache_L))
+        return fail(UG_ERR_SHAPE, "ug_qkv_rope_bf16: rows [%d, %d) do not fit a cache of %d rows", cache_row_offset, cache_row_offset + L, cache_L);
+    int major = 0;
+    const int sms = sm_count(&major);
+    if (major != 10) return fail(UG_ERR_DEVICE, "ug_qkv_rope_bf16 needs an sm_100 device (tcgen05), found compute capability %d.x", major);
+    ugk::GemmArgs g;
+    g.a = a; g.w = w_qkv; g.bias = bias_qkv; g.out = qkv_out;
+    g.lda = lda; g.ldw = ldw; g.ldo = ldo;
+    g.M = M; g.N = N; g.K = K; g.mode = ugk::kGemmQkvRope;
+    g.rope_cos = cos; g.rope_sin = sin; g.kv_cache = kv_cache_bf16;
+    g.rope_L = L; g.rope_Hq = Hq; g.rope_Hkv = Hkv; g.cache_L = cache_L; g.cache_row0 = cache_row_offset;
+    char msg[256] = "";
+    const int rc = ugk::launch_gemm_tc(g, sms, static_cast<cudaStream_t>(stream), msg, sizeof msg);
+    if (rc != 0) return fail(rc, "ug_qkv_rope_bf16: %s", msg);
+    return UG_OK;
+}

@@ -238,3 +238,35 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     _lib.check(_lib.lib().ug_gemm_bf16(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), M, N, K,
                                        a.stride(0), w.stride(0), out.stride(0), mode, _stream()))
     return out
+
+
+def qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, bias_qkv: Optional[torch.Tensor], cos: torch.Tensor, sin: torch.Tensor,
+             L: int, Hq: int, Hkv: int, kv_cache: Optional[torch.Tensor] = None, cache_row_offset: int = 0,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused q/k/v projection + RoPE (+ K/V-cache update): bf16 a [M,K] -> bf16 qkv [M,(Hq+2Hkv)*128] with the q and k
+    heads rotated (row m = position m % L; cos/sin fp32 [L,64]); with `kv_cache` (bf16 [M/L, cache_L, 2, Hkv, 128]) the
+    rotated k and the v rows also land in cache rows [cache_row_offset, cache_row_offset + L).  One launch instead of
+    `gemm` + `rope_qk_`."""
+    _need_cuda(a, w_qkv, bias_qkv, cos, sin, kv_cache)
+    M, K = a.shape
+    N = (Hq + 2 * Hkv) * 128
+    if a.dtype != torch.bfloat16 or w_qkv.dtype != torch.bfloat16 or a.stride(1) != 1 or w_qkv.stride(1) != 1 \
+            or tuple(w_qkv.shape) != (N, K):
+        raise ValueError("a must be bf16 [M,K] and w_qkv bf16 [(Hq+2Hkv)*128, K], rows contiguous")
+    if cos.dtype != torch.float32 or tuple(cos.shape) != (L, 64) or not cos.is_contiguous() or sin.shape != cos.shape \
+            or sin.dtype != torch.float32 or not sin.is_contiguous():
+        raise ValueError("cos/sin must be contiguous fp32 [L, 64]")
+    cache_L = 0
+    if kv_cache is not None:
+        if kv_cache.dtype != torch.bfloat16 or not kv_cache.is_contiguous() or tuple(kv_cache.shape[2:]) != (2, Hkv, 128) \
+                or kv_cache.shape[0] * L != M:
+            raise ValueError("kv_cache must be contiguous bf16 [M/L, cache_L, 2, Hkv, 128]")
+        cache_L = kv_cache.shape[1]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    elif tuple(out.shape) != (M, N) or out.dtype != torch.bfloat16 or out.stride(1) != 1:
+        raise ValueError("out must be bf16 [M, (Hq+2Hkv)*128] with contiguous rows")
+    _lib.check(_lib.lib().ug_qkv_rope_bf16(_ptr(a), _ptr(w_qkv), _ptr(bias_qkv), _ptr(out), M, K, a.stride(0), w_qkv.stride(0),
+                                           out.stride(0), _ptr(cos), _ptr(sin), L, Hq, Hkv, _ptr(kv_cache), cache_L,
+                                           int(cache_row_offset), _stream()))
+    return out

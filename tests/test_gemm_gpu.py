@@ -109,6 +109,44 @@ def test_gemm_tail_split_matches_cublas(M, N):
     _check(got, F.linear(a.float(), w.float()))
 
 
+@pytest.mark.parametrize("B,L,Hq,Hkv,K,with_cache", [(2, 111, 12, 2, 1536, True), (3, 70, 2, 1, 256, True), (1, 300, 12, 2, 1536, False),
+                                                        (16, 130, 12, 2, 1536, True), (2, 257, 6, 1, 128, True)])
+def test_qkv_rope_fused_matches_unfused(B, L, Hq, Hkv, K, with_cache):
+    """ug_qkv_rope_bf16 against the unfused sequence it replaces (plain GEMM + ug_rope_qk) and against the fp32 formula
+    of transformers' apply_rotary_pos_emb.  The rotation may contract its multiply-adds differently from the row kernel,
+    so equality is demanded within one bf16 ulp and on >= 99.9 % of the elements exactly."""
+    from oracle import backbone_oracle as BO
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(B * 1000 + L)
+    D, M = 128, B * L
+    N = (Hq + 2 * Hkv) * D
+    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g).bfloat16()
+    Lc, row0 = L + 37, 37
+    cos, sin = BO.rope_cos_sin(Lc, D, 1e6, dev)
+    cos_w, sin_w = cos[row0:, : D // 2].contiguous(), sin[row0:, : D // 2].contiguous()      # positions row0 .. row0+L-1
+    cache_f = torch.zeros(B, Lc, 2, Hkv, D, dtype=torch.bfloat16, device=dev) if with_cache else None
+    cache_u = torch.zeros_like(cache_f) if with_cache else None
+    fused = ops.qkv_rope(a, w, bias, cos_w, sin_w, L, Hq, Hkv, kv_cache=cache_f, cache_row_offset=row0)
+    unf = ops.gemm(a, w, bias)
+    ops.rope_qk_(unf, cos_w, sin_w, L, Hq, Hkv, D, kv_cache=cache_u, cache_row_offset=row0)
+    d = (fused.float() - unf.float()).abs()
+    assert (d <= unf.float().abs() * 2 ** -7 + 1e-6).all()
+    assert (fused == unf).float().mean().item() >= 0.999
+    assert torch.equal(fused[:, (Hq + Hkv) * D:], unf[:, (Hq + Hkv) * D:])          # v heads: untouched by the rotation
+    if with_cache:
+        assert torch.equal(cache_f[:, row0:].reshape(M, 2 * Hkv * D), fused[:, Hq * D:])
+        assert int(cache_f[:, :row0].abs().sum()) == 0
+    # fp32 formula
+    x = F.linear(a.float(), w.float(), bias.float())
+    q = x[:, : Hq * D].view(B, L, Hq, D)
+    ref_q = BO.apply_rope(q, cos[row0:], sin[row0:])
+    got_q = fused[:, : Hq * D].view(B, L, Hq, D).float()
+    assert ((got_q - ref_q).norm() / ref_q.norm()).item() <= 6e-3
+
+
 def test_gemm_rejects_bad_shapes():
     ops = _ops()
     from ml_unigen_b200._lib import UnigenB200Error

@@ -33,14 +33,14 @@ def main():
     ap.add_argument("--m", type=int, default=16 * 1026)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default="gpurun_out/gemm_bench.json")
-    ap.add_argument("--shapes", default="gate_up,qkv,o,down,head,o_resid,down_resid")
+    ap.add_argument("--shapes", default="gate_up,qkv,o,down,head,qkv_rope")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
     M = a.m
     shapes = {"gate_up": (17920, 1536, "swiglu"), "qkv": (2048, 1536, "bias"), "o": (1536, 1536, "plain"),
               "down": (1536, 8960, "plain"), "head": (8192, 1536, "plain"),
-              "o_resid": (1536, 1536, "resid"), "down_resid": (1536, 8960, "resid")}
+              "o_resid": (1536, 1536, "resid"), "down_resid": (1536, 8960, "resid"), "qkv_rope": (2048, 1536, "rope")}
     res = []
     for name in a.shapes.split(","):
         N, K, kind = shapes[name]
@@ -61,6 +61,21 @@ def main():
             t_lin = timed(lambda i: F.linear(x, ws[i % ncopies]), a.iters)
             t_own = timed(lambda i: ops.gemm(x, packed[i % ncopies], mode=ops.GEMM_SWIGLU, out=out_a), a.iters)
             t_own_plain = timed(lambda i: ops.gemm(x, ws[i % ncopies], out=out_u), a.iters)
+        elif kind == "rope":
+            from oracle import backbone_oracle as BO
+            L = 1026
+            cos, sin = BO.rope_cos_sin(L, 128, 1e6, dev)
+            cos, sin = cos[:, :64].contiguous(), sin[:, :64].contiguous()
+            bias = (0.02 * torch.randn(N, device=dev, generator=g)).bfloat16()
+            caches = [torch.zeros(M // L, L, 2, 2, 128, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+            out_p = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            ref = ops.rope_qk_(F.linear(x, ws[0], bias), cos, sin, L, 12, 2, 128, kv_cache=caches[0])
+            got = ops.qkv_rope(x, ws[0], bias, cos, sin, L, 12, 2, kv_cache=caches[1])
+            ref32 = ref[:512].float()
+            t_ref = timed(lambda i: ops.rope_qk_(F.linear(x, ws[i % ncopies], bias), cos, sin, L, 12, 2, 128, kv_cache=caches[0]), a.iters)
+            t_lin = timed(lambda i: F.linear(x, ws[i % ncopies], bias), a.iters)
+            t_own = timed(lambda i: ops.qkv_rope(x, ws[i % ncopies], bias, cos, sin, L, 12, 2, kv_cache=caches[1], out=out_p), a.iters)
+            t_own_plain = timed(lambda i: ops.gemm(x, ws[i % ncopies], bias, out=out_p), a.iters)
         elif kind == "resid":
             # unfused: cuBLAS GEMM, then add+RMSNorm with the delta; fused: residual-mode GEMM, then RMSNorm alone
             xs = torch.randn(M, N, device=dev, generator=g)
