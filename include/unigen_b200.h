@@ -169,13 +169,10 @@ int ug_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64
  *                         the unfused autocast path holds) and w = Wg / Wu interleaved in blocks of 128 rows:
  *                         w[256 j + i] = Wg[128 j + i], w[256 j + 128 + i] = Wu[128 j + i], i < 128 (`pack_gate_up`
  *                         in ml_unigen_b200.ops does this once at load time); bias must be NULL
- *   mode UG_GEMM_RESIDUAL: out fp32 [M,N] (row stride ldo floats) += bf16(a w^T + bias): the residual add that follows
- *                         o_proj and down_proj (`hidden_states = residual + hidden_states`), on the fp32 residual stream
  * Supported: N % 256 == 0, K % 64 == 0, strides multiples of 8 elements, 16-byte aligned bases; fp32 accumulation.
  */
 #define UG_GEMM_PLAIN 0
 #define UG_GEMM_SWIGLU 1
-#define UG_GEMM_RESIDUAL 2
 int ug_gemm_bf16(const void* a, const void* w, const void* bias, void* out, int M, int N, int K,
                  int64_t lda, int64_t ldw, int64_t ldo, int mode, void* stream);
 

@@ -57,8 +57,6 @@ struct GemmParams {
     int mode;
     int n_rounds, tail_tiles, split_tail;     // see the unit scheduler in the kernel
     const __nv_bfloat16* bias;
-    float* resid;                             // residual mode: fp32 [M, N], row stride ld_resid
-    int64_t ld_resid;
     // q/k/v + RoPE mode: row m is position m % rope_L of batch m / rope_L; cos/sin fp32 [rope_L, 64]
     const float* rope_cos;
     const float* rope_sin;
@@ -491,10 +489,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 for (int hh = h0; hh < h1; ++hh) {
                     const uint32_t acc_h = acc + (half < 0 ? (uint32_t)hh * 128u : 0u);
                     const int col0 = nb * kGN + hh * 128;             // first output column of this 128-column half
-                    if (MODE == kGemmPlain) {
-                        if (issuer) bulk_wait_read0();
-                        epi_bar();
-                    }
+                    if (issuer) bulk_wait_read0();
+                    epi_bar();
 #pragma unroll 1
                     for (int cc = 2 * cg; cc < 2 * cg + 2; ++cc) {
                         uint32_t v[32];
@@ -519,36 +515,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
                             for (int q = 0; q < 16; ++q) o[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
                         }
-                        if (MODE == kGemmPlain) {
+                        {
                             uint8_t* panel = stg + (cc >> 1) * 16384 + stg_row;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const uint32_t chunk = (uint32_t)((cc & 1) * 4 + j);
                                 *reinterpret_cast<uint4*>(panel + ((chunk ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                             }
-                        } else if (m0 + r < p.M) {
-                            // residual mode: x[row, col0 + 32 cc ..] += the bf16-rounded output (what `x += delta` of the
-                            // unfused path adds); each thread owns 128 contiguous bytes of its row
-                            float4* xp = reinterpret_cast<float4*>(p.resid + (int64_t)(m0 + r) * p.ld_resid + col0 + cc * 32);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float4 xv = xp[j];
-                                xv.x += __uint_as_float(o[2 * j] << 16);
-                                xv.y += __uint_as_float(o[2 * j] & 0xffff0000u);
-                                xv.z += __uint_as_float(o[2 * j + 1] << 16);
-                                xv.w += __uint_as_float(o[2 * j + 1] & 0xffff0000u);
-                                xp[j] = xv;
-                            }
                         }
                     }
-                    if (MODE == kGemmPlain) {
-                        fence_async_smem();
-                        epi_bar();
-                        if (issuer && m0 < p.M) {
-                            tma_store_2d(&tm_o, s_u32(stg), col0, m0);
-                            tma_store_2d(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
-                            bulk_commit();
-                        }
+                    fence_async_smem();
+                    epi_bar();
+                    if (issuer && m0 < p.M) {
+                        tma_store_2d(&tm_o, s_u32(stg), col0, m0);
+                        tma_store_2d(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
+                        bulk_commit();
                     }
                 }
             }
@@ -598,7 +579,7 @@ bool make_map_2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t ro
 
 int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* msg, size_t msg_len)
 {
-    if (g.mode != kGemmPlain && g.mode != kGemmSwiGLU && g.mode != kGemmResidual && g.mode != kGemmQkvRope) { snprintf(msg, msg_len, "gemm: unsupported mode %d", g.mode); return -4; }
+    if (g.mode != kGemmPlain && g.mode != kGemmSwiGLU && g.mode != kGemmQkvRope) { snprintf(msg, msg_len, "gemm: unsupported mode %d", g.mode); return -4; }
     if (g.M < 1 || g.N < kGN || g.N % kGN || g.K < kGK || g.K % kGK) {
         snprintf(msg, msg_len, "gemm: need N %% 256 == 0 and K %% 64 == 0 (M=%d N=%d K=%d)", g.M, g.N, g.K);
         return -4;
@@ -608,10 +589,9 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     if (!enc) { snprintf(msg, msg_len, "cuTensorMapEncodeTiled entry point not available"); return -6; }
     const int n_out = g.mode == kGemmSwiGLU ? g.N / 2 : g.N;
     CUtensorMap ta, tw, twh, to;
-    const bool resid = g.mode == kGemmResidual;        // the fp32 residual stream is updated with plain loads/stores: the out map is unused
     if (!make_map_2d(enc, &ta, g.a, g.M, g.K, g.lda) || !make_map_2d(enc, &tw, g.w, g.N, g.K, g.ldw) ||
         !make_map_2d(enc, &twh, g.w, g.N, g.K, g.ldw, 64) ||
-        !make_map_2d(enc, &to, resid ? g.a : g.out, g.M, resid ? g.K : n_out, resid ? g.lda : g.ldo)) {
+        !make_map_2d(enc, &to, g.out, g.M, n_out, g.ldo)) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled rejected the a/w/out layout");
         return -3;
     }
@@ -622,8 +602,6 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     p.n_kblk = g.K / kGK;
     p.mode = g.mode;
     p.bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
-    p.resid = resid ? reinterpret_cast<float*>(g.out) : nullptr;
-    p.ld_resid = g.ldo;
     p.rope_cos = g.rope_cos; p.rope_sin = g.rope_sin;
     p.kv_cache = reinterpret_cast<__nv_bfloat16*>(g.kv_cache);
     p.rope_L = g.rope_L; p.rope_Hq = g.rope_Hq; p.rope_Hkv = g.rope_Hkv; p.cache_L = g.cache_L; p.cache_row0 = g.cache_row0;
@@ -635,7 +613,6 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmSwiGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmResidual>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmQkvRope>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
@@ -652,7 +629,6 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     switch (g.mode) {
         case kGemmPlain: gemm_tc_kernel<kGemmPlain><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
         case kGemmSwiGLU: gemm_tc_kernel<kGemmSwiGLU><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
-        case kGemmResidual: gemm_tc_kernel<kGemmResidual><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
         default: gemm_tc_kernel<kGemmQkvRope><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
     }
     cudaError_t e = cudaGetLastError();

@@ -10,7 +10,6 @@ namespace ugk {
 enum GemmMode : int {
     kGemmPlain = 0,     // out bf16 [M,N]   = A W^T (+ bias)
     kGemmSwiGLU = 1,    // out bf16 [M,N/2] = silu(g) * u, W rows interleaved in blocks of 128: [g_0..127 | u_0..127 | g_128.. ]
-    kGemmResidual = 2,  // x fp32 [M,N]    += bf16(A W^T (+ bias))       (residual stream updated in place)
     kGemmQkvRope = 3,   // out bf16 [M,N]   = rope(A W^T + bias) on the q and k heads (head_dim 128), v heads copied; k/v rows also
                         // written to the K/V cache
 };

@@ -284,7 +284,7 @@ extern "C" int ug_gemm_bf16(const void* a, const void* w, const void* bias, void
                             int64_t lda, int64_t ldw, int64_t ldo, int mode, void* stream)
 {
     if (!a || !w || !out) return fail(UG_ERR_NULL, "ug_gemm_bf16: null pointer");
-    if (mode != UG_GEMM_PLAIN && mode != UG_GEMM_SWIGLU && mode != UG_GEMM_RESIDUAL) return fail(UG_ERR_SHAPE, "ug_gemm_bf16: unknown mode %d", mode);
+    if (mode != UG_GEMM_PLAIN && mode != UG_GEMM_SWIGLU) return fail(UG_ERR_SHAPE, "ug_gemm_bf16: unknown mode %d", mode);
     if (mode == UG_GEMM_SWIGLU && bias) return fail(UG_ERR_SHAPE, "ug_gemm_bf16: the SwiGLU mode takes no bias");
     if (M < 1 || N < 256 || N % 256 || K < 64 || K % 64)
         return fail(UG_ERR_SHAPE, "ug_gemm_bf16: need M >= 1, N %% 256 == 0, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);

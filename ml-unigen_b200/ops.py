@@ -200,7 +200,7 @@ def embed_rows(table: torch.Tensor, tokens: torch.Tensor, out: Optional[torch.Te
     return out
 
 
-GEMM_PLAIN, GEMM_SWIGLU, GEMM_RESIDUAL = 0, 1, 2
+GEMM_PLAIN, GEMM_SWIGLU = 0, 1
 
 
 def pack_gate_up(w_gate: torch.Tensor, w_up: torch.Tensor) -> torch.Tensor:
@@ -215,8 +215,7 @@ def pack_gate_up(w_gate: torch.Tensor, w_up: torch.Tensor) -> torch.Tensor:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, mode: int = GEMM_PLAIN,
          out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """bf16 a [M,K] x w [N,K]^T on the tcgen05 kernel.  mode GEMM_PLAIN: bf16 [M,N] (+bias);
-    GEMM_SWIGLU: w from `pack_gate_up`, returns bf16 [M,N/2] = silu(gate) * up;
-    GEMM_RESIDUAL: `out` is the fp32 residual stream [M,N], updated in place: out += bf16(a w^T + bias)."""
+    GEMM_SWIGLU: w from `pack_gate_up`, returns bf16 [M,N/2] = silu(gate) * up."""
     _need_cuda(a, w, bias)
     if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or a.dim() != 2 or w.dim() != 2:
         raise ValueError("a and w must be 2-D bf16")
@@ -227,11 +226,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if w.shape[1] != K:
         raise ValueError("inner dimensions differ")
     n_out = N // 2 if mode == GEMM_SWIGLU else N
-    if mode == GEMM_RESIDUAL:
-        if out is None or out.shape != (M, N) or out.dtype != torch.float32 or out.stride(1) != 1:
-            raise ValueError("GEMM_RESIDUAL needs out = the fp32 residual stream [M, N] with contiguous rows")
-        _need_cuda(out)
-    elif out is None:
+    if out is None:
         out = torch.empty(M, n_out, dtype=torch.bfloat16, device=a.device)
     elif out.shape != (M, n_out) or out.dtype != torch.bfloat16 or out.stride(1) != 1:
         raise ValueError("out must be bf16 [M, n_out] with contiguous rows")

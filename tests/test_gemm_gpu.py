@@ -75,24 +75,6 @@ def test_gemm_swiglu(M, I, K):
     assert ((got.float() - unf.float()).norm() / unf.float().norm()).item() <= 4e-3
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 512, 1536), (2082, 1536, 8960), (16 * 1026, 1536, 1536), (5000, 5120, 256)])
-@pytest.mark.parametrize("with_bias", [False, True])
-def test_gemm_residual(M, N, K, with_bias):
-    """x += bf16(a w^T + bias), fp32 x: equal to the unfused `x += plain GEMM output` bit for bit (same GEMM, same rounding)."""
-    ops = _ops()
-    dev = torch.device("cuda:0")
-    g = torch.Generator(device=dev).manual_seed(M + N + K)
-    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
-    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
-    b = torch.randn(N, device=dev, generator=g).bfloat16() if with_bias else None
-    x0 = torch.randn(M, N, device=dev, generator=g)
-    x = x0.clone()
-    ops.gemm(a, w, b, mode=ops.GEMM_RESIDUAL, out=x)
-    plain = ops.gemm(a, w, b)
-    assert torch.equal(x, x0 + plain.float())
-    _check(plain, F.linear(a.float(), w.float(), None if b is None else b.float()))
-
-
 @pytest.mark.parametrize("M,N", [(16 * 1026, 1536), (16 * 1026, 2048), (9000, 768), (700, 256)])
 def test_gemm_tail_split_matches_cublas(M, N):
     """Shapes whose last round is cut into 256 x 128 half tiles (N = 128 MMAs): every output element still equals the

@@ -40,7 +40,7 @@ def main():
     M = a.m
     shapes = {"gate_up": (17920, 1536, "swiglu"), "qkv": (2048, 1536, "bias"), "o": (1536, 1536, "plain"),
               "down": (1536, 8960, "plain"), "head": (8192, 1536, "plain"),
-              "o_resid": (1536, 1536, "resid"), "down_resid": (1536, 8960, "resid"), "qkv_rope": (2048, 1536, "rope")}
+              "qkv_rope": (2048, 1536, "rope")}
     res = []
     for name in a.shapes.split(","):
         N, K, kind = shapes[name]
@@ -76,22 +76,6 @@ def main():
             t_lin = timed(lambda i: F.linear(x, ws[i % ncopies], bias), a.iters)
             t_own = timed(lambda i: ops.qkv_rope(x, ws[i % ncopies], bias, cos, sin, L, 12, 2, kv_cache=caches[1], out=out_p), a.iters)
             t_own_plain = timed(lambda i: ops.gemm(x, ws[i % ncopies], bias, out=out_p), a.iters)
-        elif kind == "resid":
-            # unfused: cuBLAS GEMM, then add+RMSNorm with the delta; fused: residual-mode GEMM, then RMSNorm alone
-            xs = torch.randn(M, N, device=dev, generator=g)
-            gain = torch.ones(N, device=dev, dtype=torch.bfloat16)
-            x1, x2 = xs.clone(), xs.clone()
-            ref = ops.add_rmsnorm(x1, gain, 1e-6, F.linear(x, ws[0]))
-            ops.gemm(x, ws[0], mode=ops.GEMM_RESIDUAL, out=x2)
-            got = ops.add_rmsnorm(x2, gain, 1e-6, None)
-            ref32 = ref[:512].float()
-            t_ref = timed(lambda i: ops.add_rmsnorm(x1, gain, 1e-6, F.linear(x, ws[i % ncopies])), a.iters)
-            t_lin = timed(lambda i: F.linear(x, ws[i % ncopies]), a.iters)
-            def fused(i):
-                ops.gemm(x, ws[i % ncopies], mode=ops.GEMM_RESIDUAL, out=x2)
-                ops.add_rmsnorm(x2, gain, 1e-6, None)
-            t_own = timed(fused, a.iters)
-            t_own_plain = timed(lambda i: ops.gemm(x, ws[i % ncopies], mode=ops.GEMM_RESIDUAL, out=x2), a.iters)
         else:
             ref = F.linear(x, ws[0], bias)
             got = ops.gemm(x, ws[0], bias)
