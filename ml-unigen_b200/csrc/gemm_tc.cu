@@ -609,13 +609,15 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
         snprintf(msg, msg_len, "gemm: q/k/v + RoPE mode needs cos/sin tables, rope_L >= 1 and N == (Hq + 2 Hkv) * 128");
         return -4;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                       // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmSwiGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmQkvRope>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int max_clusters = num_sms / 2 > 0 ? num_sms / 2 : 1;
     const int n_tiles = p.n_mblk * p.n_nblk;

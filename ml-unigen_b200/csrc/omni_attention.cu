@@ -792,11 +792,13 @@ int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, c
         p.n_split = k;
     }
     p.dbg = g_attn_dbg;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                       // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(omni_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttn2Smem);
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     dim3 grid((unsigned)(p.n_qpairs * a.Hq * a.B + p.n_split));
     omni_attention_kernel<<<grid, kAttn2Threads, kAttn2Smem, stream>>>(tq, tqt, tk, tv, p);

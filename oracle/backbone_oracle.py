@@ -126,3 +126,28 @@ def smoke_attention(dev) -> None:
     err = (out - ref).abs().max().item()
     assert err < 2e-2, f"omni attention max-abs error {err}"
     print(f"smoke: omni attention max-abs error {err:.3e} vs fp32 reference")
+
+
+def smoke_gemm(dev) -> None:
+    """One small fused gate|up + SwiGLU launch and one q/k/v + RoPE launch of the tcgen05 linear-layer kernel on the GPU
+    against the fp32 formulas (used by __graft_entry__.smoke)."""
+    from ml_unigen_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    M, K, I = 300, 256, 384
+    x = torch.randn(M, K, generator=g).bfloat16().to(dev)
+    wg = (torch.randn(I, K, generator=g) * K ** -0.5).bfloat16().to(dev)
+    wu = (torch.randn(I, K, generator=g) * K ** -0.5).bfloat16().to(dev)
+    got = ops.gemm(x, ops.pack_gate_up(wg, wu), mode=ops.GEMM_SWIGLU).float()
+    ref = torch.nn.functional.silu(x.float() @ wg.float().T) * (x.float() @ wu.float().T)
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 8e-3, f"fused SwiGLU GEMM relative L2 error {rel}"
+    B, L, Hq, Hkv, D = 2, 150, 2, 1, 128
+    w = (torch.randn((Hq + 2 * Hkv) * D, K, generator=g) * K ** -0.5).bfloat16().to(dev)
+    b = torch.randn((Hq + 2 * Hkv) * D, generator=g).bfloat16().to(dev)
+    cos, sin = rope_cos_sin(L, D, 1e6, dev)
+    qkv = ops.qkv_rope(x, w, b, cos[:, : D // 2].contiguous(), sin[:, : D // 2].contiguous(), L, Hq, Hkv)
+    full = torch.nn.functional.linear(x.float(), w.float(), b.float())
+    ref_q = apply_rope(full[:, : Hq * D].view(B, L, Hq, D), cos, sin)
+    rel_q = ((qkv[:, : Hq * D].view(B, L, Hq, D).float() - ref_q).norm() / ref_q.norm()).item()
+    assert rel_q < 6e-3, f"fused q/k/v + RoPE relative L2 error {rel_q}"
+    print(f"smoke: tcgen05 GEMM epilogues: SwiGLU rel-L2 {rel:.2e}, q/k/v + RoPE rel-L2 {rel_q:.2e} vs fp32 formulas")
