@@ -246,6 +246,32 @@ def run_ours(args):
     # timed region 2: end to end through the public API from pinned host memory
     t_e2e, _ = timed(args.steps, True)
 
+    # after the measured path: the MAGViT-v2 pixel decoder on the generated token grids (reported
+    # separately -- BASELINE.json's images/s counts token grids)
+    pix = None
+    if rank == 0 and not args.no_pixels:
+        from ml_unigen_b200.magvit import MagvitV2DecoderB200
+        from ml_unigen_b200 import callers
+        dec = MagvitV2DecoderB200.random_init(dev, seed=0)
+        grid = callers.clamp_token_ids(one_generation(2000, False), V)
+        for _ in range(2):
+            dec.decode_code(grid)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(3):
+            img = dec.decode_code(grid)
+        p1.record()
+        torch.cuda.synchronize()
+        pix_ms = p0.elapsed_time(p1) / 3
+        pix = {"ms_per_batch": pix_ms, "images": int(grid.shape[0]), "pixels": f"{img.shape[-2]}x{img.shape[-1]}",
+               "images_per_s_decoder_alone": grid.shape[0] / pix_ms * 1e3,
+               "note": "MagvitV2DecoderB200.decode_code (NHWC bf16; cuDNN convolutions, hand-written LFQ unpack / GroupNorm+swish / "
+                       "upsample kernels), random-init weights of the default architecture; not part of `value`"}
+        del dec, img
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
         peaks = _peaks()
         images = gB * args.steps
@@ -312,6 +338,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(host_out.numel() * 8)},
             "gpu_launches": launches_per_gen * args.steps,
         }
+        if pix is not None:
+            pix["images_per_s_tokens_plus_pixels"] = (e - s) / (t_dev / args.steps + pix["ms_per_batch"] * 1e-3)
+            line["pixel_decoder"] = pix
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -327,6 +356,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=1024)
     ap.add_argument("--timesteps", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pixels", action="store_true", help="skip the MAGViT-v2 pixel-decoder timing after the measured path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -186,6 +186,22 @@ int ug_qkv_rope_bf16(const void* a, const void* w_qkv, const void* bias_qkv, voi
                      int64_t lda, int64_t ldw, int64_t ldo, const float* cos, const float* sin, int L, int Hq, int Hkv,
                      void* kv_cache_bf16 /* nullable */, int cache_L, int cache_row_offset, void* stream);
 
+/* ---- MAGViT-v2 pixel decoder, memory-bound kernels -----------------------------
+ * MAGVITv2.decode_code (models/multimodal_encoder/magvitv2.py:438-442) = LFQuantizer.get_codebook_entry (:217-230) +
+ * VQGANDecoder.forward (:371-408).  Activations are NHWC bf16; the convolutions between these kernels are cuDNN.
+ *   ug_lfq_unpack_bf16      : z bf16 [n, dim] = +-1, channel c = bit (dim-1-c) of ids[n] (the `embedding` buffer of the
+ *                             reference, never materialised)
+ *   ug_groupnorm_nhwc_bf16  : y = GroupNorm(32 groups, eps)(x) * gamma + beta, then y * sigmoid(y) when swish != 0
+ *                             (common_modules.py:19-27); x, y bf16 [B, HW, C] (may alias), C % 32 == 0, C % 8 == 0,
+ *                             256 % (C/8) == 0; workspace fp32 of ug_groupnorm_workspace_floats(B, HW, C) elements
+ *   ug_upsample2x_nhwc_bf16 : F.interpolate(scale_factor=2, mode="nearest") (common_modules.py:40), [B,H,W,C] -> [B,2H,2W,C]
+ */
+int ug_lfq_unpack_bf16(const int64_t* ids, void* z_bf16, int64_t n, int dim, void* stream);
+size_t ug_groupnorm_workspace_floats(int B, int64_t HW, int C);
+int ug_groupnorm_nhwc_bf16(const void* x_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16, float* workspace,
+                           int B, int64_t HW, int C, float eps, int swish, void* stream);
+int ug_upsample2x_nhwc_bf16(const void* x_bf16, void* y_bf16, int B, int H, int W, int C, void* stream);
+
 /* test hook: float[2*128*128 + 2048] receiving the raw scores S and the bf16 probabilities P of the first kv tile
  * of the first query tile of (b=0, h=0), followed by 2048 cycle stamps of CTA (0,0,0) (tools/attn_timeline.py), of
  * subsequent ug_omni_attention_bf16 calls of this thread; NULL = off */

@@ -1,0 +1,188 @@
+// magvit_ops.cu -- the memory-bound kernels of MAGVITv2.decode_code (apple/ml-unigen
+// models/multimodal_encoder/magvitv2.py:217-230 LFQ codebook entry; common_modules.py:19-43 swish, GroupNorm(32, 1e-6),
+// nearest-2x Upsample) for NHWC bf16 activations.  The convolutions between them are cuDNN (torch.nn.functional.conv2d on
+// channels_last tensors): plain library convolutions, like the plain cuBLAS GEMMs of the backbone.
+//   * lfq_unpack:   13 bits of a token id -> 13 values +-1 (no embedding table is read);
+//   * GroupNorm+swish: ONE statistics pass (per-block partial sums per group, combined in double by a tiny finalize
+//     kernel: deterministic, no atomics on global memory) and ONE apply pass that also applies x*sigmoid(x) -- the
+//     reference runs group_norm (2 passes), sigmoid and mul as separate ATen kernels (5 passes over the activation);
+//   * upsample2x: every input vector is read once and written four times.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "magvit_ops.h"
+
+namespace ugk {
+namespace {
+
+constexpr int kGroups = 32;
+constexpr int kGnThreads = 256;
+constexpr int kGnRowsPerBlock = 256;          // spatial positions per statistics block
+
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(256) lfq_unpack_kernel(const int64_t* __restrict__ ids, __nv_bfloat16* __restrict__ z, int64_t n, int dim)
+{
+    const int64_t total = n * dim;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = idx / dim;
+        const int c = (int)(idx - t * dim);
+        const int64_t id = ids[t];
+        z[idx] = __float2bfloat16(((id >> (dim - 1 - c)) & 1) ? 1.0f : -1.0f);
+    }
+}
+
+// grid (chunks, B); block kGnThreads.  Thread t owns vector slot t % (C/8) (8 consecutive channels) of the rows
+// t / (C/8) + k * (kGnThreads / (C/8)) of its chunk.  Requires C % 8 == 0 and kGnThreads % (C/8) == 0.
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int64_t HW, int C)
+{
+    __shared__ float s_part[kGnThreads * 8], q_part[kGnThreads * 8];
+    const int vecs = C / 8;
+    const int slot = threadIdx.x % vecs, row0 = threadIdx.x / vecs, rstep = kGnThreads / vecs;
+    const int b = blockIdx.y;
+    const int64_t r_begin = (int64_t)blockIdx.x * kGnRowsPerBlock;
+    const int64_t r_end = min(r_begin + (int64_t)kGnRowsPerBlock, HW);
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.0f; q[e] = 0.0f; }
+    const uint4* xb = x + (int64_t)b * HW * vecs;
+    for (int64_t r = r_begin + row0; r < r_end; r += rstep) {
+        const uint4 v = xb[r * vecs + slot];
+        const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s_part[threadIdx.x * 8 + e] = s[e]; q_part[threadIdx.x * 8 + e] = q[e]; }
+    __syncthreads();
+    // fixed-order block reduction (no atomics: the result does not depend on scheduling): thread g adds the partial sums
+    // of the C/32 channels of group g over the kGnThreads/(C/8) row lanes -- 64 terms whatever C is
+    if (threadIdx.x < kGroups) {
+        const int g = threadIdx.x, cpg = C / kGroups;
+        float ts = 0.0f, tq = 0.0f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+            for (int k = 0; k < rstep; ++k) {
+                const int t = (c >> 3) + vecs * k;
+                ts += s_part[t * 8 + (c & 7)];
+                tq += q_part[t * 8 + (c & 7)];
+            }
+        float* p = partial + (((int64_t)b * gridDim.x + blockIdx.x) * kGroups + g) * 2;
+        p[0] = ts;
+        p[1] = tq;
+    }
+}
+
+// grid B, block 32: thread g combines the chunk partials of group g in double, fixed order
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int chunks, double inv_count, float eps)
+{
+    const int b = blockIdx.x, g = threadIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int c = 0; c < chunks; ++c) {
+        const float* p = partial + (((int64_t)b * chunks + c) * kGroups + g) * 2;
+        s += (double)p[0];
+        q += (double)p[1];
+    }
+    const double mean = s * inv_count;
+    double var = q * inv_count - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    stats[(b * kGroups + g) * 2] = (float)mean;
+    stats[(b * kGroups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                                                       const __nv_bfloat16* __restrict__ beta, const float* __restrict__ stats,
+                                                       uint4* __restrict__ y, int64_t HW, int C, int B, int swish)
+{
+    const int vecs = C / 8, cpg = C / kGroups;
+    const int64_t per_b = HW * vecs, total = per_b * B;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / per_b);
+        const int slot = (int)(idx % vecs);
+        const uint4 v = x[idx];
+        const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = slot * 8 + e;
+            const int g = c / cpg;
+            const float mean = stats[(b * kGroups + g) * 2], rstd = stats[(b * kGroups + g) * 2 + 1];
+            float t = (f[e] - mean) * rstd * __bfloat162float(gamma[c]) + __bfloat162float(beta[c]);
+            if (swish) t = __fdividef(t, 1.0f + __expf(-t));
+            o[e] = t;
+        }
+        y[idx] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+    }
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W, int vecs)
+{
+    const int64_t total = (int64_t)B * H * W * vecs;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % vecs);
+        const int64_t pix = idx / vecs;
+        const int xx = (int)(pix % W);
+        const int yy = (int)((pix / W) % H);
+        const int64_t b = pix / ((int64_t)W * H);
+        const uint4 val = x[idx];
+        uint4* o = y + (((b * 2 * H + 2 * yy) * 2 * W) + 2 * xx) * (int64_t)vecs + v;
+        o[0] = val;
+        o[vecs] = val;
+        o[(int64_t)2 * W * vecs] = val;
+        o[(int64_t)2 * W * vecs + vecs] = val;
+    }
+}
+
+unsigned grid_for(int64_t total, int threads)
+{
+    int64_t g = (total + threads - 1) / threads;
+    const int64_t cap = 148 * 16;
+    return (unsigned)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+}  // namespace
+
+cudaError_t launch_lfq_unpack(const int64_t* ids, void* z, int64_t n, int dim, cudaStream_t stream)
+{
+    if (n < 1 || dim < 1 || dim > 62) return cudaErrorInvalidValue;
+    lfq_unpack_kernel<<<grid_for(n * dim, 256), 256, 0, stream>>>(ids, reinterpret_cast<__nv_bfloat16*>(z), n, dim);
+    return cudaGetLastError();
+}
+
+size_t groupnorm_workspace_floats(int B, int64_t HW, int C)
+{
+    (void)C;
+    const int64_t chunks = (HW + kGnRowsPerBlock - 1) / kGnRowsPerBlock;
+    return (size_t)B * (size_t)chunks * kGroups * 2 + (size_t)B * kGroups * 2;
+}
+
+cudaError_t launch_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, void* y, float* workspace, int B, int64_t HW,
+                                  int C, float eps, int swish, cudaStream_t stream)
+{
+    if (B < 1 || HW < 1 || C % kGroups != 0 || C % 8 != 0 || kGnThreads % (C / 8) != 0) return cudaErrorInvalidValue;
+    const int chunks = (int)((HW + kGnRowsPerBlock - 1) / kGnRowsPerBlock);
+    float* partial = workspace;
+    float* stats = workspace + (size_t)B * chunks * kGroups * 2;
+    gn_stats_kernel<<<dim3((unsigned)chunks, (unsigned)B), kGnThreads, 0, stream>>>(reinterpret_cast<const uint4*>(x), partial, HW, C);
+    gn_finalize_kernel<<<B, kGroups, 0, stream>>>(partial, stats, chunks, 1.0 / ((double)HW * (C / kGroups)), eps);
+    gn_apply_kernel<<<grid_for((int64_t)B * HW * (C / 8), 256), 256, 0, stream>>>(
+        reinterpret_cast<const uint4*>(x), reinterpret_cast<const __nv_bfloat16*>(gamma), reinterpret_cast<const __nv_bfloat16*>(beta),
+        stats, reinterpret_cast<uint4*>(y), HW, C, B, swish);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, cudaStream_t stream)
+{
+    if (B < 1 || H < 1 || W < 1 || C % 8 != 0) return cudaErrorInvalidValue;
+    upsample2x_kernel<<<grid_for((int64_t)B * H * W * (C / 8), 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                                       reinterpret_cast<uint4*>(y), B, H, W, C / 8);
+    return cudaGetLastError();
+}
+
+}  // namespace ugk

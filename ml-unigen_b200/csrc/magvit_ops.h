@@ -1,0 +1,20 @@
+// magvit_ops.h -- memory-bound kernels of the MAGViT-v2 pixel decoder, NHWC bf16.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ugk {
+
+// ids int64 [n] -> z bf16 [n, dim] (= NHWC [B,h,w,dim]): +-1, channel c = bit (dim-1-c) of the index
+cudaError_t launch_lfq_unpack(const int64_t* ids, void* z_bf16, int64_t n, int dim, cudaStream_t stream);
+
+// GroupNorm(32 groups, eps) (+ swish) over x bf16 NHWC [B, HW, C]; partial: fp32 [B, chunks, 32, 2] scratch, stats: fp32 [B, 32, 2]
+size_t groupnorm_workspace_floats(int B, int64_t HW, int C);
+cudaError_t launch_groupnorm_nhwc(const void* x_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16,
+                                  float* workspace, int B, int64_t HW, int C, float eps, int swish, cudaStream_t stream);
+
+// nearest-neighbour 2x upsampling, NHWC bf16 [B,H,W,C] -> [B,2H,2W,C]
+cudaError_t launch_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int B, int H, int W, int C, cudaStream_t stream);
+
+}  // namespace ugk

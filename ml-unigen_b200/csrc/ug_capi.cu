@@ -9,6 +9,7 @@
 #include "omni_attention.h"
 #include "backbone_ops.h"
 #include "gemm_tc.h"
+#include "magvit_ops.h"
 
 float* ugk_debug_rowsum_out();
 int ugk_debug_force_full_race();
@@ -333,5 +334,43 @@ extern "C" int ug_qkv_rope_bf16(const void* a, const void* w_qkv, const void* bi
     char msg[256] = "";
     const int rc = ugk::launch_gemm_tc(g, sms, static_cast<cudaStream_t>(stream), msg, sizeof msg);
     if (rc != 0) return fail(rc, "ug_qkv_rope_bf16: %s", msg);
+    return UG_OK;
+}
+
+extern "C" int ug_lfq_unpack_bf16(const int64_t* ids, void* z_bf16, int64_t n, int dim, void* stream)
+{
+    if (!ids || !z_bf16) return fail(UG_ERR_NULL, "ug_lfq_unpack_bf16: null pointer");
+    if (n < 1 || dim < 1 || dim > 62) return fail(UG_ERR_SHAPE, "ug_lfq_unpack_bf16: bad shape");
+    cudaError_t e = ugk::launch_lfq_unpack(ids, z_bf16, n, dim, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_lfq_unpack_bf16 launch");
+    return UG_OK;
+}
+
+extern "C" size_t ug_groupnorm_workspace_floats(int B, int64_t HW, int C)
+{
+    if (B < 1 || HW < 1 || C < 1) return 0;
+    return ugk::groupnorm_workspace_floats(B, HW, C);
+}
+
+extern "C" int ug_groupnorm_nhwc_bf16(const void* x_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16, float* workspace,
+                                      int B, int64_t HW, int C, float eps, int swish, void* stream)
+{
+    if (!x_bf16 || !gamma_bf16 || !beta_bf16 || !y_bf16 || !workspace) return fail(UG_ERR_NULL, "ug_groupnorm_nhwc_bf16: null pointer");
+    if (B < 1 || HW < 1 || C < 32 || C % 32 || C % 8 || 256 % (C / 8))
+        return fail(UG_ERR_SHAPE, "ug_groupnorm_nhwc_bf16: need C %% 32 == 0 and 256 %% (C/8) == 0 (C=%d)", C);
+    if (!aligned16(x_bf16) || !aligned16(y_bf16)) return fail(UG_ERR_ALIGN, "ug_groupnorm_nhwc_bf16: x and y must be 16-byte aligned");
+    cudaError_t e = ugk::launch_groupnorm_nhwc(x_bf16, gamma_bf16, beta_bf16, y_bf16, workspace, B, HW, C, eps, swish,
+                                               static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_groupnorm_nhwc_bf16 launch");
+    return UG_OK;
+}
+
+extern "C" int ug_upsample2x_nhwc_bf16(const void* x_bf16, void* y_bf16, int B, int H, int W, int C, void* stream)
+{
+    if (!x_bf16 || !y_bf16) return fail(UG_ERR_NULL, "ug_upsample2x_nhwc_bf16: null pointer");
+    if (B < 1 || H < 1 || W < 1 || C < 8 || C % 8) return fail(UG_ERR_SHAPE, "ug_upsample2x_nhwc_bf16: need C %% 8 == 0");
+    if (!aligned16(x_bf16) || !aligned16(y_bf16)) return fail(UG_ERR_ALIGN, "ug_upsample2x_nhwc_bf16: pointers must be 16-byte aligned");
+    cudaError_t e = ugk::launch_upsample2x_nhwc(x_bf16, y_bf16, B, H, W, C, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_upsample2x_nhwc_bf16 launch");
     return UG_OK;
 }

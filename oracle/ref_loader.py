@@ -148,3 +148,13 @@ def build_reference_unigen(cfg_dir: str, vocab_size: int, codebook_size: int, nu
                       load_from_pretrained=True)
     model.llm.config._attn_implementation = "sdpa"
     return model.eval()
+
+
+def load_magvitv2():
+    """models/multimodal_encoder/magvitv2.py (+ common_modules.py), unmodified, under the stand-ins above.
+    Returns the module (VQGANDecoder, LFQuantizer, MAGVITv2).  `models/misc.py` (config helpers over omegaconf /
+    jaxtyping / typeguard, absent here and unused by the decoder) is replaced by an empty stand-in."""
+    _install_stubs()
+    if "models.misc" not in sys.modules:
+        sys.modules["models.misc"] = types.ModuleType("models.misc")
+    return importlib.import_module("models.multimodal_encoder.magvitv2")
