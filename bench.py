@@ -249,7 +249,7 @@ def run_ours(args):
     # after the measured path: the MAGViT-v2 pixel decoder on the generated token grids (reported
     # separately -- BASELINE.json's images/s counts token grids)
     pix = None
-    if rank == 0 and not args.no_pixels:
+    if world == 1 and not args.no_pixels:           # N = 1 only: one_generation() holds a collective at N > 1
         from ml_unigen_b200.magvit import MagvitV2DecoderB200
         from ml_unigen_b200 import callers
         dec = MagvitV2DecoderB200.random_init(dev, seed=0)
@@ -269,8 +269,6 @@ def run_ours(args):
                "note": "MagvitV2DecoderB200.decode_code (NHWC bf16; cuDNN convolutions, hand-written LFQ unpack / GroupNorm+swish / "
                        "upsample kernels), random-init weights of the default architecture; not part of `value`"}
         del dec, img
-    if world > 1:
-        dist.barrier()
 
     if rank == 0:
         peaks = _peaks()
