@@ -86,3 +86,35 @@ def test_select_topk_candidates():
     assert idx.tolist() == [1, 2, 5, 4] and torch.equal(t, ids[idx]) and s.tolist() == scores[idx].tolist()
     t, s, idx = callers.select_topk_candidates(ids[:2], scores[:2], topk=4)
     assert idx.tolist() == [1, 0]
+
+
+def test_pack_gate_up_layout():
+    """Host-side weight packing of the fused gate|up + SwiGLU GEMM (ml_unigen_b200.ops.pack_gate_up): block 2j of 128 rows
+    = gate rows [128j, 128j+128), block 2j+1 = the same rows of up (include/unigen_b200.h, UG_GEMM_SWIGLU)."""
+    from ml_unigen_b200 import ops
+    I, K = 384, 16
+    wg = torch.arange(I * K, dtype=torch.float32).view(I, K)
+    wu = -torch.arange(I * K, dtype=torch.float32).view(I, K) - 1
+    w = ops.pack_gate_up(wg, wu)
+    assert w.shape == (2 * I, K) and w.is_contiguous()
+    for j in range(I // 128):
+        assert torch.equal(w[256 * j: 256 * j + 128], wg[128 * j: 128 * j + 128])
+        assert torch.equal(w[256 * j + 128: 256 * j + 256], wu[128 * j: 128 * j + 128])
+    with pytest.raises(ValueError):
+        ops.pack_gate_up(wg[:100], wu[:100])
+    with pytest.raises(ValueError):
+        ops.pack_gate_up(wg, wu[:256])
+
+
+def test_kernels_refuse_cpu_tensors():
+    """No CPU fallback: every tensor-level wrapper raises on host tensors instead of computing something else."""
+    from ml_unigen_b200 import ops, magvit, _lib
+    a = torch.zeros(256, 64, dtype=torch.bfloat16)
+    w = torch.zeros(256, 64, dtype=torch.bfloat16)
+    with pytest.raises(_lib.UnigenB200Error):
+        ops.gemm(a, w)
+    with pytest.raises(_lib.UnigenB200Error):
+        magvit.lfq_unpack(torch.zeros(1, 16, dtype=torch.int64))
+    with pytest.raises(_lib.UnigenB200Error):
+        magvit.groupnorm_swish(torch.zeros(1, 4, 4, 32, dtype=torch.bfloat16), torch.ones(32, dtype=torch.bfloat16),
+                               torch.zeros(32, dtype=torch.bfloat16))
