@@ -21,6 +21,7 @@ laid out for one B200:
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -73,6 +74,7 @@ class QwenBackboneB200:
                 wd=bf(weights[p + "mlp.down_proj.weight"]),
             ))
         self._rope_cache = {}
+        self.own_plain_gemms = os.environ.get("UG_PLAIN_GEMM", "cublas") == "own"      # experiment switch, see DESIGN.md 4.5
         self.attn_events = None        # bench hook: list receiving (start, end) CUDA events of every attention launch
         self.mlp_events = None         # bench hook: the same for every fused gate|up + SwiGLU GEMM launch
 
@@ -150,10 +152,10 @@ class QwenBackboneB200:
                 k = qkv[:, Hq * D: (Hq + Hkv) * D].view(B, L, Hkv, D)
                 v = qkv[:, (Hq + Hkv) * D:].view(B, L, Hkv, D)
             a = self._attention(q, k, v, pad_len, soi_idx, scale, 0)
-            o = F.linear(a.view(M, Hq * D), ly["wo"])
+            o = self._plain_linear(a.view(M, Hq * D), ly["wo"])
             h = ops.add_rmsnorm(x2, ly["ln2"], cfg.rms_norm_eps, o)
             act = self._gate_up(h, ly["wgu"])
-            delta = F.linear(act, ly["wd"])
+            delta = self._plain_linear(act, ly["wd"])
         hn = ops.add_rmsnorm(x2, self.final_norm, cfg.rms_norm_eps, delta).view(B, L, H)
         return hn if rows is None else hn[:, rows]
 
@@ -189,12 +191,16 @@ class QwenBackboneB200:
             q = qkv[:, : Hq * D].view(B, Ls, Hq, D)
             k, v = kv_cache[li][:, :, 0], kv_cache[li][:, :, 1]
             a = self._attention(q, k, v, pad_len, soi_idx, scale, s0)
-            o = F.linear(a.view(M, Hq * D), ly["wo"])
+            o = self._plain_linear(a.view(M, Hq * D), ly["wo"])
             h = ops.add_rmsnorm(x2, ly["ln2"], cfg.rms_norm_eps, o)
             act = self._gate_up(h, ly["wgu"])
-            delta = F.linear(act, ly["wd"])
+            delta = self._plain_linear(act, ly["wd"])
         hn = ops.add_rmsnorm(x2, self.final_norm, cfg.rms_norm_eps, delta).view(B, Ls, H)
         return hn if rows is None else hn[:, rows]
+
+    def _plain_linear(self, a, w):
+        """o_proj / down_proj: plain GEMMs with nothing to fuse."""
+        return ops.gemm(a, w) if self.own_plain_gemms else F.linear(a, w)
 
     def _gate_up(self, h, wgu):
         ev = self.mlp_events
