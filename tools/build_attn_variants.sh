@@ -7,6 +7,6 @@ python build.py > /dev/null
 for v in "$@"; do
   name=$(echo "$v" | tr -c 'A-Za-z0-9\n' '_')
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include $v -c omni_attention.cu -o ../../build/exp/oa_$name.o
-  nvcc -gencode arch=compute_100a,code=sm_100a --shared -Xcompiler -fPIC -o ../../build/exp/lib_$name.so ug_capi.o decode_step.o decode_fast.o backbone_ops.o gemm_tc.o ../../build/exp/oa_$name.o -lcuda
+  nvcc -gencode arch=compute_100a,code=sm_100a --shared -Xcompiler -fPIC -o ../../build/exp/lib_$name.so ug_capi.o decode_step.o decode_fast.o backbone_ops.o gemm_tc.o magvit_ops.o ../../build/exp/oa_$name.o -lcuda
   echo built build/exp/lib_$name.so
 done
