@@ -6,6 +6,10 @@
 //   * GroupNorm+swish: ONE statistics pass (per-block partial sums per group, combined in double by a tiny finalize
 //     kernel: deterministic, no atomics on global memory) and ONE apply pass that also applies x*sigmoid(x) -- the
 //     reference runs group_norm (2 passes), sigmoid and mul as separate ATen kernels (5 passes over the activation);
+//   * the per-channel bias of a convolution is never a pass of its own (torch adds it with a 326 us non-vectorised
+//     broadcast kernel per convolution at 16 x 512 x 512 x 128): it is added inside the GroupNorm that consumes the
+//     convolution (statistics and apply kernels take an input bias), or together with the residual add of the ResnetBlock
+//     (bias_add: out = conv2 + b2 + shortcut (+ b_shortcut), one pass);
 //   * upsample2x: every input vector is read once and written four times.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -41,7 +45,8 @@ __global__ void __launch_bounds__(256) lfq_unpack_kernel(const int64_t* __restri
 
 // grid (chunks, B); block kGnThreads.  Thread t owns vector slot t % (C/8) (8 consecutive channels) of the rows
 // t / (C/8) + k * (kGnThreads / (C/8)) of its chunk.  Requires C % 8 == 0 and kGnThreads % (C/8) == 0.
-__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int64_t HW, int C)
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ in_bias,
+                                                              float* __restrict__ partial, int64_t HW, int C)
 {
     __shared__ float s_part[kGnThreads * 8], q_part[kGnThreads * 8];
     const int vecs = C / 8;
@@ -53,11 +58,18 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __res
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.0f; q[e] = 0.0f; }
     const uint4* xb = x + (int64_t)b * HW * vecs;
+    float ib[8];                                   // per-channel bias of the producing convolution (added here instead of in a pass of its own)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ib[e] = in_bias ? __bfloat162float(in_bias[slot * 8 + e]) : 0.0f;
     for (int64_t r = r_begin + row0; r < r_end; r += rstep) {
         const uint4 v = xb[r * vecs + slot];
         const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+        for (int e = 0; e < 8; ++e) {
+            const float t = f[e] + ib[e];
+            s[e] += t;
+            q[e] = fmaf(t, t, q[e]);
+        }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s_part[threadIdx.x * 8 + e] = s[e]; q_part[threadIdx.x * 8 + e] = q[e]; }
@@ -96,7 +108,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __r
     stats[(b * kGroups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ in_bias,
+                                                       const __nv_bfloat16* __restrict__ gamma,
                                                        const __nv_bfloat16* __restrict__ beta, const float* __restrict__ stats,
                                                        uint4* __restrict__ y, int64_t HW, int C, int B, int swish)
 {
@@ -113,11 +126,36 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
             const int c = slot * 8 + e;
             const int g = c / cpg;
             const float mean = stats[(b * kGroups + g) * 2], rstd = stats[(b * kGroups + g) * 2 + 1];
-            float t = (f[e] - mean) * rstd * __bfloat162float(gamma[c]) + __bfloat162float(beta[c]);
+            const float xin = f[e] + (in_bias ? __bfloat162float(in_bias[c]) : 0.0f);
+            float t = (xin - mean) * rstd * __bfloat162float(gamma[c]) + __bfloat162float(beta[c]);
             if (swish) t = __fdividef(t, 1.0f + __expf(-t));
             o[e] = t;
         }
         y[idx] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+    }
+}
+
+// out = a + bias_a[c] (+ r (+ bias_r[c])): the bias of the last convolution of a ResnetBlock and its residual add in ONE pass
+__global__ void __launch_bounds__(256) bias_add_kernel(const uint4* __restrict__ a, const __nv_bfloat16* __restrict__ bias_a,
+                                                       const uint4* __restrict__ r, const __nv_bfloat16* __restrict__ bias_r,
+                                                       uint4* __restrict__ out, int64_t rows, int vecs)
+{
+    const int64_t total = rows * vecs;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int slot = (int)(idx % vecs);
+        const uint4 va = a[idx];
+        float f[8] = {bf_lo(va.x), bf_hi(va.x), bf_lo(va.y), bf_hi(va.y), bf_lo(va.z), bf_hi(va.z), bf_lo(va.w), bf_hi(va.w)};
+        if (bias_a) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += __bfloat162float(bias_a[slot * 8 + e]);
+        }
+        if (r) {
+            const uint4 vr = r[idx];
+            const float g[8] = {bf_lo(vr.x), bf_hi(vr.x), bf_lo(vr.y), bf_hi(vr.y), bf_lo(vr.z), bf_hi(vr.z), bf_lo(vr.w), bf_hi(vr.w)};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += g[e] + (bias_r ? __bfloat162float(bias_r[slot * 8 + e]) : 0.0f);
+        }
+        out[idx] = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
     }
 }
 
@@ -162,18 +200,29 @@ size_t groupnorm_workspace_floats(int B, int64_t HW, int C)
     return (size_t)B * (size_t)chunks * kGroups * 2 + (size_t)B * kGroups * 2;
 }
 
-cudaError_t launch_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, void* y, float* workspace, int B, int64_t HW,
-                                  int C, float eps, int swish, cudaStream_t stream)
+cudaError_t launch_groupnorm_nhwc(const void* x, const void* in_bias, const void* gamma, const void* beta, void* y, float* workspace,
+                                  int B, int64_t HW, int C, float eps, int swish, cudaStream_t stream)
 {
     if (B < 1 || HW < 1 || C % kGroups != 0 || C % 8 != 0 || kGnThreads % (C / 8) != 0) return cudaErrorInvalidValue;
     const int chunks = (int)((HW + kGnRowsPerBlock - 1) / kGnRowsPerBlock);
     float* partial = workspace;
     float* stats = workspace + (size_t)B * chunks * kGroups * 2;
-    gn_stats_kernel<<<dim3((unsigned)chunks, (unsigned)B), kGnThreads, 0, stream>>>(reinterpret_cast<const uint4*>(x), partial, HW, C);
+    gn_stats_kernel<<<dim3((unsigned)chunks, (unsigned)B), kGnThreads, 0, stream>>>(
+        reinterpret_cast<const uint4*>(x), reinterpret_cast<const __nv_bfloat16*>(in_bias), partial, HW, C);
     gn_finalize_kernel<<<B, kGroups, 0, stream>>>(partial, stats, chunks, 1.0 / ((double)HW * (C / kGroups)), eps);
     gn_apply_kernel<<<grid_for((int64_t)B * HW * (C / 8), 256), 256, 0, stream>>>(
-        reinterpret_cast<const uint4*>(x), reinterpret_cast<const __nv_bfloat16*>(gamma), reinterpret_cast<const __nv_bfloat16*>(beta),
-        stats, reinterpret_cast<uint4*>(y), HW, C, B, swish);
+        reinterpret_cast<const uint4*>(x), reinterpret_cast<const __nv_bfloat16*>(in_bias), reinterpret_cast<const __nv_bfloat16*>(gamma),
+        reinterpret_cast<const __nv_bfloat16*>(beta), stats, reinterpret_cast<uint4*>(y), HW, C, B, swish);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bias_add_nhwc(const void* a, const void* bias_a, const void* r, const void* bias_r, void* out, int64_t rows, int C,
+                                 cudaStream_t stream)
+{
+    if (rows < 1 || C % 8 != 0) return cudaErrorInvalidValue;
+    bias_add_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, stream>>>(
+        reinterpret_cast<const uint4*>(a), reinterpret_cast<const __nv_bfloat16*>(bias_a), reinterpret_cast<const uint4*>(r),
+        reinterpret_cast<const __nv_bfloat16*>(bias_r), reinterpret_cast<uint4*>(out), rows, C / 8);
     return cudaGetLastError();
 }
 

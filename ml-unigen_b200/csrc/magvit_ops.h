@@ -11,8 +11,13 @@ cudaError_t launch_lfq_unpack(const int64_t* ids, void* z_bf16, int64_t n, int d
 
 // GroupNorm(32 groups, eps) (+ swish) over x bf16 NHWC [B, HW, C]; partial: fp32 [B, chunks, 32, 2] scratch, stats: fp32 [B, 32, 2]
 size_t groupnorm_workspace_floats(int B, int64_t HW, int C);
-cudaError_t launch_groupnorm_nhwc(const void* x_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16,
+// in_bias (nullable, bf16 [C]) is added to x first: the bias of the convolution that produced x
+cudaError_t launch_groupnorm_nhwc(const void* x_bf16, const void* in_bias_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16,
                                   float* workspace, int B, int64_t HW, int C, float eps, int swish, cudaStream_t stream);
+
+// out = a + bias_a[c] (+ r (+ bias_r[c])), bf16 [rows, C]; bias_a, r, bias_r nullable; out may alias a or r
+cudaError_t launch_bias_add_nhwc(const void* a_bf16, const void* bias_a_bf16, const void* r_bf16, const void* bias_r_bf16, void* out_bf16,
+                                 int64_t rows, int C, cudaStream_t stream);
 
 // nearest-neighbour 2x upsampling, NHWC bf16 [B,H,W,C] -> [B,2H,2W,C]
 cudaError_t launch_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int B, int H, int W, int C, cudaStream_t stream);

@@ -48,17 +48,38 @@ _gn_ws = _GroupNormWorkspace()
 
 
 def groupnorm_swish(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6, swish: bool = True,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x bf16 NHWC [B,H,W,C] (contiguous) -> GroupNorm(32, eps)(x)*gamma+beta, then y*sigmoid(y) if `swish`."""
-    ops._need_cuda(x, gamma, beta)
+                    out: Optional[torch.Tensor] = None, in_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 NHWC [B,H,W,C] (contiguous) -> GroupNorm(32, eps)(x + in_bias)*gamma+beta, then y*sigmoid(y) if `swish`.
+    `in_bias` (bf16 [C]): the bias of the convolution that produced x, folded into this pass."""
+    ops._need_cuda(x, gamma, beta, in_bias)
     B, H, W, C = x.shape
     if x.dtype != torch.bfloat16 or not x.is_contiguous() or gamma.dtype != torch.bfloat16 or beta.dtype != torch.bfloat16:
         raise ValueError("x must be contiguous bf16 NHWC, gamma/beta bf16 [C]")
     if out is None:
         out = torch.empty_like(x)
     ws = _gn_ws.get(B, H * W, C, x.device)
-    _lib.check(_lib.lib().ug_groupnorm_nhwc_bf16(ops._ptr(x), ops._ptr(gamma), ops._ptr(beta), ops._ptr(out), ops._ptr(ws),
+    if in_bias is not None and (in_bias.dtype != torch.bfloat16 or in_bias.numel() != C or not in_bias.is_contiguous()):
+        raise ValueError("in_bias must be contiguous bf16 [C]")
+    _lib.check(_lib.lib().ug_groupnorm_nhwc_bf16(ops._ptr(x), ops._ptr(in_bias), ops._ptr(gamma), ops._ptr(beta), ops._ptr(out), ops._ptr(ws),
                                                  B, H * W, C, float(eps), 1 if swish else 0, ops._stream()))
+    return out
+
+
+def bias_add(a: torch.Tensor, bias_a: Optional[torch.Tensor], r: Optional[torch.Tensor] = None,
+             bias_r: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = a + bias_a (+ r (+ bias_r)) on bf16 NHWC tensors [.., C] in one pass (default: in place on `a`)."""
+    ops._need_cuda(a, bias_a, r, bias_r)
+    C = a.shape[-1]
+    if a.dtype != torch.bfloat16 or not a.is_contiguous() or (r is not None and (r.shape != a.shape or not r.is_contiguous()
+                                                                                   or r.dtype != torch.bfloat16)):
+        raise ValueError("a (and r) must be contiguous bf16 tensors of the same shape")
+    for b in (bias_a, bias_r):
+        if b is not None and (b.dtype != torch.bfloat16 or b.numel() != C or not b.is_contiguous()):
+            raise ValueError("biases must be contiguous bf16 [C]")
+    if out is None:
+        out = a
+    _lib.check(_lib.lib().ug_bias_add_nhwc_bf16(ops._ptr(a), ops._ptr(bias_a), ops._ptr(r), ops._ptr(bias_r), ops._ptr(out),
+                                                a.numel() // C, C, ops._stream()))
     return out
 
 
@@ -73,8 +94,10 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def _conv(x_nhwc: torch.Tensor, w: torch.Tensor, b: torch.Tensor, padding: int) -> torch.Tensor:
-    """cuDNN convolution on an NHWC bf16 activation; returns NHWC (contiguous)."""
+def _conv(x_nhwc: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], padding: int) -> torch.Tensor:
+    """cuDNN convolution on an NHWC bf16 activation; returns NHWC (contiguous).  The big convolutions are called with
+    b = None: torch adds a convolution bias in a separate, non-vectorised broadcast kernel (326 us per convolution at
+    16 x 512 x 512 x 128 -- a third of the decoder before it was folded into the consuming kernels)."""
     y = F.conv2d(x_nhwc.permute(0, 3, 1, 2), w, b, padding=padding)        # NCHW view of channels_last memory
     return y.permute(0, 2, 3, 1).contiguous()                                # no copy when cuDNN kept channels_last
 
@@ -145,12 +168,13 @@ class MagvitV2DecoderB200:
     def _res(self, p: str, x: torch.Tensor) -> torch.Tensor:
         w = self.w
         h = groupnorm_swish(x, w[p + "norm1.weight"], w[p + "norm1.bias"])
-        h = _conv(h, w[p + "conv1.weight"], w[p + "conv1.bias"], 1)
-        h = groupnorm_swish(h, w[p + "norm2.weight"], w[p + "norm2.bias"], out=h)
-        h = _conv(h, w[p + "conv2.weight"], w[p + "conv2.bias"], 1)
+        h = _conv(h, w[p + "conv1.weight"], None, 1)
+        h = groupnorm_swish(h, w[p + "norm2.weight"], w[p + "norm2.bias"], out=h, in_bias=w[p + "conv1.bias"])
+        h = _conv(h, w[p + "conv2.weight"], None, 1)
         if p + "nin_shortcut.weight" in w:
-            x = _conv(x, w[p + "nin_shortcut.weight"], w[p + "nin_shortcut.bias"], 0)
-        return h.add_(x)
+            xs = _conv(x, w[p + "nin_shortcut.weight"], None, 0)
+            return bias_add(h, w[p + "conv2.bias"], xs, w[p + "nin_shortcut.bias"])
+        return bias_add(h, w[p + "conv2.bias"], x)
 
     def _attn(self, p: str, x: torch.Tensor) -> torch.Tensor:
         w = self.w
@@ -180,7 +204,7 @@ class MagvitV2DecoderB200:
                 h = self._res(f"up.{lvl}.block.{i}.", h)
             if lvl != 0:
                 h = upsample2x(h)
-                h = _conv(h, w[f"up.{lvl}.upsample.conv.weight"], w[f"up.{lvl}.upsample.conv.bias"], 1)
+                h = bias_add(_conv(h, w[f"up.{lvl}.upsample.conv.weight"], None, 1), w[f"up.{lvl}.upsample.conv.bias"])
         h = groupnorm_swish(h, w["norm_out.weight"], w["norm_out.bias"], out=h)
         h = _conv(h, w["conv_out.weight"], w["conv_out.bias"], 1)
         return h.permute(0, 3, 1, 2).float()

@@ -53,6 +53,28 @@ def test_groupnorm_swish(dev, B, H, W, C, swish):
     assert torch.equal(x2, y)
 
 
+def test_groupnorm_input_bias_and_bias_add(dev):
+    from ml_unigen_b200 import magvit
+    g = torch.Generator(device=dev).manual_seed(9)
+    B, H, W, C = 2, 40, 24, 128
+    x = torch.randn(B, H, W, C, device=dev, generator=g).bfloat16()
+    r = torch.randn(B, H, W, C, device=dev, generator=g).bfloat16()
+    b1 = torch.randn(C, device=dev, generator=g).bfloat16()
+    b2 = torch.randn(C, device=dev, generator=g).bfloat16()
+    gamma = (1 + 0.2 * torch.randn(C, device=dev, generator=g)).bfloat16()
+    beta = (0.1 * torch.randn(C, device=dev, generator=g)).bfloat16()
+    y = magvit.groupnorm_swish(x, gamma, beta, in_bias=b1)
+    xin = (x.float() + b1.float()).permute(0, 3, 1, 2)
+    ref = F.group_norm(xin, 32, gamma.float(), beta.float(), eps=1e-6)
+    ref = (ref * torch.sigmoid(ref)).permute(0, 2, 3, 1)
+    assert (y.float() - ref).abs().max().item() <= 3e-2
+    # bias + residual (+ shortcut bias): one rounding of the fp32 sum
+    out = magvit.bias_add(x.clone(), b1, r, b2)
+    assert torch.equal(out, (x.float() + b1.float() + (r.float() + b2.float())).bfloat16())
+    assert torch.equal(magvit.bias_add(x.clone(), b1, r), (x.float() + b1.float() + r.float()).bfloat16())
+    assert torch.equal(magvit.bias_add(x.clone(), b1), (x.float() + b1.float()).bfloat16())
+
+
 def test_upsample2x_exact(dev):
     from ml_unigen_b200 import magvit
     x = torch.randn(2, 5, 7, 64, device=dev).bfloat16()
