@@ -108,6 +108,12 @@ void ug_debug_set_decode_mode(int mode);
  * exactly, [1] rows evaluated exhaustively, [2] mask selections with an undecided band, [3] rows replayed for it, [4..7] reasons of [1] (degenerate row, bound not reached, list A / B overflow) */
 void ug_debug_set_decode_stats(unsigned* counters);
 
+/* Classifier-free guidance as a pass of its own, in place on the conditional logits (models/unigen.py:410 under autocast, op by op
+ * in bf16): cond[i] = bf16(bf16(scale * bf16(cond[i] - uncond[i])) + uncond[i]) for n bf16 elements (n % 8 == 0) -- exactly the
+ * values ug_decode_step_bf16 forms inline when it is given uncond_logits.  The result is bf16 again, so a following
+ * ug_decode_step_bf16(logits = cond, uncond_logits = NULL) runs the certified fast kernel and returns the same ids and masks. */
+int ug_cfg_mix_bf16(void* cond_logits_inout, const void* uncond_logits, float guidance_scale, int64_t n, void* stream);
+
 /* ---- omni attention --------------------------------------------------------------------------
  * out = softmax(q k^T * scale + M) v per head, with the omni mask M given in closed form by two
  * integers per sequence:

@@ -569,4 +569,30 @@ cudaError_t launch_export_noise(uint64_t seed, uint64_t offset, int64_t batch_of
     return cudaGetLastError();
 }
 
+// classifier-free guidance as a pass of its own, in place on the conditional logits: x = bf16(bf16(s * bf16(c - u)) + u), the
+// op-by-op bf16 arithmetic of models/unigen.py:410 under autocast (ug::cfg_mix_bits, the expression the exact kernel applies
+// inline).  The mixed logits are bf16 values again, so the certified fast kernel can stream them: CFG costs one extra
+// elementwise pass instead of the exact kernel (the shipped evaluation configs all run with guidance_scale > 1).
+__global__ void __launch_bounds__(256) cfg_mix_kernel(uint4* __restrict__ cond, const uint4* __restrict__ uncond, float scale, int64_t n_vec)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 c = cond[i], u = uncond[i];
+        const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, uw[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            o[w] = ug::cfg_mix_bits(cw[w] & 0xffffu, uw[w] & 0xffffu, scale) | (ug::cfg_mix_bits(cw[w] >> 16, uw[w] >> 16, scale) << 16);
+        cond[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+cudaError_t launch_cfg_mix(void* cond_inout, const void* uncond, float scale, int64_t n, cudaStream_t stream)
+{
+    if (n < 8 || n % 8) return cudaErrorInvalidValue;
+    int64_t blocks = (n / 8 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cfg_mix_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<uint4*>(cond_inout), static_cast<const uint4*>(uncond), scale, n / 8);
+    return cudaGetLastError();
+}
+
 }  // namespace ugk

@@ -41,4 +41,7 @@ cudaError_t launch_topk(const DecodeArgs& a, const int64_t* mask_len, cudaStream
 cudaError_t launch_export_noise(uint64_t seed, uint64_t offset, int64_t batch_offset, int B, int N, int V,
                                 float* q_out, float* u_out, cudaStream_t stream);
 
+// cond[i] = bf16(bf16(scale * bf16(cond[i] - uncond[i])) + uncond[i]) in place, n bf16 elements (n % 8 == 0)
+cudaError_t launch_cfg_mix(void* cond_inout, const void* uncond, float scale, int64_t n, cudaStream_t stream);
+
 }  // namespace ugk

@@ -387,3 +387,13 @@ extern "C" int ug_upsample2x_nhwc_bf16(const void* x_bf16, void* y_bf16, int B, 
     if (e != cudaSuccess) return cuda_fail(e, "ug_upsample2x_nhwc_bf16 launch");
     return UG_OK;
 }
+
+extern "C" int ug_cfg_mix_bf16(void* cond_logits_inout, const void* uncond_logits, float guidance_scale, int64_t n, void* stream)
+{
+    if (!cond_logits_inout || !uncond_logits) return fail(UG_ERR_NULL, "ug_cfg_mix_bf16: null pointer");
+    if (n < 8 || n % 8) return fail(UG_ERR_SHAPE, "ug_cfg_mix_bf16: the element count must be a positive multiple of 8");
+    if (!aligned16(cond_logits_inout) || !aligned16(uncond_logits)) return fail(UG_ERR_ALIGN, "ug_cfg_mix_bf16: pointers must be 16-byte aligned");
+    cudaError_t e = ugk::launch_cfg_mix(cond_logits_inout, uncond_logits, guidance_scale, n, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_cfg_mix_bf16 launch");
+    return UG_OK;
+}

@@ -200,6 +200,18 @@ def embed_rows(table: torch.Tensor, tokens: torch.Tensor, out: Optional[torch.Te
     return out
 
 
+def cfg_mix_(cond_logits: torch.Tensor, uncond_logits: torch.Tensor, guidance_scale: float) -> torch.Tensor:
+    """In place on `cond_logits` (bf16, contiguous): guidance_scale * (cond - uncond) + uncond with a bf16 rounding after
+    every op (models/unigen.py:410 under autocast) -- what `decode_step(..., uncond_logits=...)` forms inline.  Afterwards
+    `decode_step(cond_logits, ...)` without `uncond_logits` takes the certified fast kernel."""
+    _need_cuda(cond_logits, uncond_logits)
+    if cond_logits.dtype != torch.bfloat16 or uncond_logits.dtype != torch.bfloat16 or cond_logits.shape != uncond_logits.shape \
+            or not cond_logits.is_contiguous() or not uncond_logits.is_contiguous() or cond_logits.numel() % 8:
+        raise ValueError("cond/uncond logits must be contiguous bf16 tensors of the same shape, element count % 8 == 0")
+    _lib.check(_lib.lib().ug_cfg_mix_bf16(_ptr(cond_logits), _ptr(uncond_logits), float(guidance_scale), cond_logits.numel(), _stream()))
+    return cond_logits
+
+
 GEMM_PLAIN, GEMM_SWIGLU = 0, 1
 
 

@@ -155,16 +155,20 @@ class UniGenB200:
             if ev is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record()
+            logits_seen = logits.clone() if trace is not None else None     # test hook: the logits before the CFG mix
+            if use_cfg:
+                # guidance in its own in-place pass (bf16 op by op, models/unigen.py:410); the mixed logits are bf16 again,
+                # so the certified fast kernel streams them (passing uncond_logits would select the exact kernel)
+                ops.cfg_mix_(logits[:B], logits[B:], float(guidance_scale))
             ops.decode_step(logits[:B], ids_img, mask_token_id=mask_id, mask_len_cap=cap, temperature=temp,
                             workspace=ws, sampled_out=sampled, mask_out=masking, sel_prob_out=sel_prob,
-                            uncond_logits=logits[B:] if use_cfg else None, guidance_scale=float(guidance_scale),
                             seed=seed, offset=base_offset + step, batch_offset=batch_offset)
             if ev is not None:
                 e1 = torch.cuda.Event(enable_timing=True)
                 e1.record()
                 ev.append((e0, e1))
             if trace is not None:                                        # test hook: what each step saw and produced
-                trace.append(dict(logits=logits.clone(), cap=cap, temperature=temp, offset=base_offset + step,
+                trace.append(dict(logits=logits_seen, cap=cap, temperature=temp, offset=base_offset + step,
                                   ids_after=ids_img.clone(), sampled=sampled.clone(), masking=masking.clone()))
         self.last_sel_prob = sel_prob
         return sampled

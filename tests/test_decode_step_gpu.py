@@ -198,6 +198,35 @@ def test_cfg_mode_bit_exact_vs_oracle(dev):
         assert np.array_equal(k["sampled"], k2["sampled"]) and np.array_equal(k["mask"], k2["mask"])
 
 
+def test_cfg_mix_pass_then_fast_kernel_equals_inline_cfg(dev):
+    """ug_cfg_mix_bf16 (guidance as an in-place pass) + the certified fast kernel == the exact kernel with inline CFG ==
+    the oracle, and the pass itself equals torch's bf16 arithmetic bit for bit (models/unigen.py:410 under autocast)."""
+    from ml_unigen_b200 import ops
+    B, N, V = 3, 64, 8192
+    gen = torch.Generator().manual_seed(21)
+    cond = (3 * torch.randn(B, N, V, generator=gen)).bfloat16()
+    uncond = (3 * torch.randn(B, N, V, generator=gen)).bfloat16()
+    cond[0, 0, :8] = torch.tensor([float("inf"), -float("inf"), 0.0, -0.0, 1e38, -1e38, 1e-38, 3.0]).bfloat16()
+    ids = torch.full((B, N), MASK_ID, dtype=torch.int64)
+    ids[1, ::5] = 7
+    for scale in (2.0, 6.0, 1.5):
+        mixed = ops.cfg_mix_(cond.to(dev).clone(), uncond.to(dev), scale)
+        ref = (scale * (cond.to(dev) - uncond.to(dev)) + uncond.to(dev))
+        same = (mixed.view(torch.int16) == ref.view(torch.int16)) | (torch.isnan(mixed) & torch.isnan(ref))
+        assert bool(same.all())
+        if scale == 1.5:
+            continue
+        clean_c, clean_u = cond.clone(), uncond.clone()
+        clean_c[0, 0, :8] = 0.0
+        k_inline = _run_kernel(clean_c, ids, dev, cap=40, temp=0.8, seed=9, offset=3, uncond=clean_u, scale=scale)
+        mixed = ops.cfg_mix_(clean_c.to(dev).clone(), clean_u.to(dev), scale).cpu()
+        k_pass = _run_kernel(mixed, ids, dev, cap=40, temp=0.8, seed=9, offset=3, mode="fast")
+        o = O.decode_step(_bits(clean_c), ids.numpy(), mask_token_id=MASK_ID, mask_len_cap=40, temperature=0.8, seed=9,
+                          offset=3, uncond_bf16=_bits(clean_u), guidance_scale=scale)
+        for key in ("sampled", "mask", "ids"):
+            assert np.array_equal(k_pass[key], o[key]) and np.array_equal(k_inline[key], o[key]), key
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_full_maskgit_loop_vs_oracle(dev, mode):
     """18 steps, N=256: the state (ids) evolves through the kernel and the oracle separately and
