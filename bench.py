@@ -229,12 +229,12 @@ def run_ours(args):
         one_generation(w, False)
     torch.cuda.synchronize()
 
-    # timed region 1: prompts resident in HBM; attention and decode launches bracketed by CUDA events
+    # instrumented region (not the headline number): the same K generations with the launches of the three roofline kernels
+    # bracketed by CUDA events; the events keep the per-step pass out of its CUDA graph, so this region runs eagerly
     model.backbone.attn_events = []
     model.backbone.mlp_events = []
     model.decode_events = []
-    sampler = ClockSampler(local) if rank == 0 else None
-    t_dev, clocks = timed(args.steps, False, sampler)
+    t_instr, _ = timed(args.steps, False)
     attn_all = [(a.elapsed_time(b), lq) for a, b, lq in model.backbone.attn_events]
     attn_ms = [t for t, lq in attn_all if lq != L]      # the per-step launches (image-block rows only)
     attn_full_ms = [t for t, lq in attn_all if lq == L] # the step-0 launches over all rows
@@ -243,7 +243,10 @@ def run_ours(args):
     model.backbone.attn_events = None
     model.backbone.mlp_events = None
     model.decode_events = None
-    # timed region 2: end to end through the public API from pinned host memory
+    # timed region 1 (`value`): prompts resident in HBM, no instrumentation
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_dev, clocks = timed(args.steps, False, sampler)
+    # timed region 2 (`e2e`): end to end through the public API from pinned host memory
     t_e2e, _ = timed(args.steps, True)
 
     # after the measured path: the MAGViT-v2 pixel decoder on the generated token grids (reported
@@ -281,7 +284,7 @@ def run_ours(args):
         attn_avg = sum(attn_ms) / len(attn_ms) * 1e-3
         dec_avg = sum(dec_ms) / len(dec_ms) * 1e-3
         achieved = flops / attn_avg / 1e12
-        attn_share = (sum(attn_ms) + sum(attn_full_ms if attn_full_ms is not attn_ms else [])) * 1e-3 / t_dev
+        attn_share = (sum(attn_ms) + sum(attn_full_ms if attn_full_ms is not attn_ms else [])) * 1e-3 / t_instr
         # own launches: embed, per layer 2 x add+RMSNorm + RoPE + attention + gate|up GEMM, final norm, head GEMM, decode rows + selection
         launches_per_gen = T * (1 + n_layers * 5 + 1 + 1 + 2)
         cfgm = model.backbone.cfg
@@ -291,7 +294,7 @@ def run_ours(args):
         mlp_avg = sum(mlp_ms) / len(mlp_ms) * 1e-3
         mlp_flops = 2.0 * m_rows * 2 * cfgm.intermediate_size * cfgm.hidden_size
         mlp_tf = mlp_flops / mlp_avg / 1e12
-        mlp_share = sum(t for t, _ in mlp_all) * 1e-3 / t_dev
+        mlp_share = sum(t for t, _ in mlp_all) * 1e-3 / t_instr
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -307,6 +310,8 @@ def run_ours(args):
                                    "guidance 0, cosine schedule (BASELINE.json configs[1])",
                        "global_batch": gB, "parallelism": f"replicas x{world}, images sharded, 1 all-gather/generation",
                        "l2": "working set (3.1 GB weights + activations) >> 126 MB L2, no flush needed",
+                       "launch": "steps 1..17 of a generation replay one CUDA graph of the per-step backbone pass; the roofline objects "
+                                 "come from an instrumented eager pass of the same K generations (%.1f ms per generation)" % (t_instr / args.steps * 1e3),
                        "gemms": "gate|up + SwiGLU and the codebook head: own tcgen05 2-CTA kernel (ug_gemm_bf16); q/k/v, o, down: cuBLAS bf16 "
                                 "(F.linear); attention, decode step and row kernels hand-written"},
             "roofline": {"kernel": "gemm_tc_kernel, SwiGLU epilogue (tcgen05 cta_group::2): gate_proj | up_proj + silu(g)*u in one launch",

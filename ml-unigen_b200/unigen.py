@@ -26,6 +26,43 @@ from .backbone import QwenBackboneB200, QwenConfig
 from .sampling import cosine_schedule
 
 
+class _StepGraph:
+    """The per-step backbone pass of the prefix-reuse path (embed the N+2 image-block rows, 28 layers, final norm, codebook
+    head) as ONE CUDA graph over static buffers.  Every launch inside it is a plain asynchronous kernel launch, so the
+    ~200 launches of a MaskGIT step replay without CPU work and with the launch-to-launch gaps of a graph."""
+
+    def __init__(self, bb: QwenBackboneB200, n_seq: int, L: int, N: int, s0: int, V: int, text_vocab: int):
+        dev = bb.device
+        self.kv_cache = bb.new_kv_cache(n_seq, L)
+        self.tok = torch.zeros(n_seq, L - s0, dtype=torch.int64, device=dev)
+        self.P = torch.zeros(n_seq, dtype=torch.int32, device=dev)
+        self.S = torch.zeros(n_seq, dtype=torch.int32, device=dev)
+        self.args = (bb, N, s0, V, text_vocab)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.logits: Optional[torch.Tensor] = None
+        self.warm = False
+
+    def _body(self):
+        bb, N, s0, V, text_vocab = self.args
+        x = bb.embed_tokens(self.tok)
+        hidden = bb.forward_suffix(x, self.P, self.S, s0, self.kv_cache, rows=slice(1, 1 + N))
+        return bb.codebook_logits(hidden, text_vocab, V)
+
+    def run(self) -> torch.Tensor:
+        if self.graph is not None:
+            self.graph.replay()
+            return self.logits
+        if not self.warm:                      # first pass eagerly: function attributes, lazily created tables and workspaces
+            self.warm = True
+            return self._body()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.logits = self._body()
+        self.graph = g
+        g.replay()
+        return self.logits
+
+
 class UniGenB200:
     def __init__(self, backbone: QwenBackboneB200, *, codebook_size: int = 8192, mask_token_id: Optional[int] = None,
                  pad_id: int = prompting.QWEN_PAD_ID, soi_id: int = prompting.QWEN_SOI_ID):
@@ -36,6 +73,8 @@ class UniGenB200:
         self.pad_id, self.soi_id = pad_id, soi_id
         self.device = backbone.device
         self._ws = {}
+        self._step_graphs = {}
+        self.use_cuda_graph = True     # replay the per-step backbone pass as a CUDA graph (off while bench hooks record events)
         self.last_sel_prob = None
         self.decode_events = None      # bench hook: (start, end) CUDA events of every decode-step launch
 
@@ -133,7 +172,17 @@ class UniGenB200:
             smin, smax = int(S.min()), int(S.max())                     # one host sync per generation
             if smin == smax and smin == L - N - 2:
                 s0 = smin
-        kv_cache = bb.new_kv_cache(tokens.shape[0], L) if s0 is not None else None
+        sg = None
+        if s0 is not None and self.use_cuda_graph and kwargs.get("cuda_graph", True) and bb.attn_events is None \
+                and bb.mlp_events is None and timesteps > 3:
+            key = (tokens.shape[0], L, N, s0, V, text_vocab_size)
+            sg = self._step_graphs.get(key)
+            if sg is None:
+                self._step_graphs.clear()                               # one shape at a time: the static buffers hold the K/V cache
+                sg = self._step_graphs[key] = _StepGraph(bb, tokens.shape[0], L, N, s0, V, text_vocab_size)
+            sg.P.copy_(P)
+            sg.S.copy_(S)
+        kv_cache = sg.kv_cache if sg is not None else (bb.new_kv_cache(tokens.shape[0], L) if s0 is not None else None)
         for step in range(timesteps):
             # tokens of the image block: mask id stays, codebook id c becomes c + text_vocab (unigen.py:451)
             img_tok = torch.where(ids_img == mask_id, ids_img, ids_img + text_vocab_size)
@@ -143,10 +192,14 @@ class UniGenB200:
             if s0 is None or step == 0:
                 x = bb.embed_tokens(tokens)
                 hidden = bb.forward(x, P, S, rows=img_rows, kv_cache=kv_cache)        # bf16 [B(2B), N, H]
+                logits = bb.codebook_logits(hidden, text_vocab_size, V)  # bf16 [B(2B), N, V]
+            elif sg is not None:
+                sg.tok.copy_(tokens[:, s0:])
+                logits = sg.run()
             else:
                 x = bb.embed_tokens(tokens[:, s0:].contiguous())
                 hidden = bb.forward_suffix(x, P, S, s0, kv_cache, rows=slice(1, 1 + N))
-            logits = bb.codebook_logits(hidden, text_vocab_size, V)      # bf16 [B(2B), N, V]
+                logits = bb.codebook_logits(hidden, text_vocab_size, V)
             ratio = 1.0 * (step + 1) / timesteps                        # unigen.py:425
             mask_ratio = noise_schedule(torch.tensor(ratio))             # unigen.py:426 (0-d CPU tensor)
             cap = int((N * mask_ratio).floor().item())                   # unigen.py:436 (host scalar, no device sync)
