@@ -77,6 +77,7 @@ class QwenBackboneB200:
         self.own_plain_gemms = os.environ.get("UG_PLAIN_GEMM", "cublas") == "own"      # experiment switch, see DESIGN.md 4.5
         self.attn_events = None        # bench hook: list receiving (start, end) CUDA events of every attention launch
         self.mlp_events = None         # bench hook: the same for every fused gate|up + SwiGLU GEMM launch
+        self.plain_events = None       # bench hook: the same for every o_proj / down_proj launch
 
     # -------------------------------------------------------------------------------------------
     @classmethod
@@ -200,7 +201,15 @@ class QwenBackboneB200:
 
     def _plain_linear(self, a, w):
         """o_proj / down_proj: plain GEMMs with nothing to fuse."""
-        return ops.gemm(a, w) if self.own_plain_gemms else F.linear(a, w)
+        ev = self.plain_events
+        if ev is None:
+            return ops.gemm(a, w) if self.own_plain_gemms else F.linear(a, w)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = ops.gemm(a, w) if self.own_plain_gemms else F.linear(a, w)
+        e1.record()
+        ev.append((e0, e1, a.shape[0], a.shape[1]))
+        return out
 
     def _gate_up(self, h, wgu):
         ev = self.mlp_events
