@@ -1,9 +1,11 @@
 // gemm_tc.cu -- the linear layers of the Qwen2 backbone (transformers Qwen2Attention / Qwen2MLP, reached from
 // apple/ml-unigen models/unigen.py:260-266) as ONE persistent tcgen05 kernel with the elementwise step that follows
 // the GEMM in the reference fused into its epilogue:
-//   mode plain   : out = x W^T (+ bias)                           q/k/v projection, codebook head
+//   mode plain   : out = x W^T (+ bias)                           codebook head (and o_proj / down_proj when selected)
 //   mode SwiGLU  : act = silu(x Wg^T) * (x Wu^T)                  Qwen2MLP.act_fn(gate_proj(x)) * up_proj(x): the
 //                  [M, 2I] gate|up activation (588 MB per layer at config 2) is never written to HBM
+//   mode q/k/v   : qkv = rope(x [Wq|Wk|Wv]^T + bias)              q_proj/k_proj/v_proj + apply_rotary_pos_emb, and the rotated
+//                  k rows / the v rows written to the K/V cache of the text-prefix reuse in the same epilogue
 //
 // Shape of the kernel (sm_100a only):
 //   * cluster of 2 CTAs = one SM pair; the pair owns a 256 x 256 output tile; `tcgen05.mma.cta_group::2.kind::f16`

@@ -10,7 +10,7 @@ namespace ugk {
 enum GemmMode : int {
     kGemmPlain = 0,     // out bf16 [M,N]   = A W^T (+ bias)
     kGemmSwiGLU = 1,    // out bf16 [M,N/2] = silu(g) * u, W rows interleaved in blocks of 128: [g_0..127 | u_0..127 | g_128.. ]
-    kGemmQkvRope = 3,   // out bf16 [M,N]   = rope(A W^T + bias) on the q and k heads (head_dim 128), v heads copied; k/v rows also
+    kGemmQkvRope = 2,   // out bf16 [M,N]   = rope(A W^T + bias) on the q and k heads (head_dim 128), v heads copied; k/v rows also
                         // written to the K/V cache
 };
 
