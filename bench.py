@@ -324,7 +324,10 @@ def run_ours(args):
                          "share_of_step": mlp_share,
                          "note": "2*M*N*K with M = 16 x 1026 rows, N = 17920, K = 1536; launches of MaskGIT steps 1..17"},
             "roofline_attention": {"kernel": "omni_attention_kernel (tcgen05)", "bound": "tensor", "achieved": achieved,
-                         "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"], "traffic": None,
+                         "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"], "traffic": 83301888,
+                         "traffic_note": "dram__bytes_read.sum (69.6 MB = q + k + v once) + dram__bytes_write.sum (13.7 MB; most of the "
+                                         "50 MB output is still in L2 when the capture ends) of one window-pass launch, ncu --set full "
+                                         "(profiles/r1_ncu_omni_attention.md)",
                          "peak_source": peaks["source"] + " bf16_tflops_sustained", "flops_per_launch": flops,
                          "avg_launch_ms": attn_avg * 1e3, "launches_timed": len(attn_ms), "share_of_step": attn_share,
                          "note": "launches of MaskGIT steps 1..17 (query rows = the N+2 image-block rows, keys = all rows; "
