@@ -53,7 +53,8 @@ def test_gemm_plain_strided_rows():
     assert out_big[:, :512].abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("M,I,K", [(128, 128, 64), (300, 256, 1536), (2082, 8960, 1536), (16 * 130, 1280, 1536)])
+@pytest.mark.parametrize("M,I,K", [(128, 128, 64), (300, 256, 1536), (2082, 8960, 1536), (16 * 130, 1280, 1536),
+                                   (16 * 258, 8960, 1536), (5000, 1024, 256), (16 * 1026, 1152, 128)])
 def test_gemm_swiglu(M, I, K):
     ops = _ops()
     dev = torch.device("cuda:0")
