@@ -282,11 +282,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 int mb, nb, half;
                 unit(ui, mb, nb, half);
                 const int m0 = mb * 256 + (int)rank * kGM;
-                // full unit: this CTA's 128 of the tile's 256 W rows.  Half unit: 64 rows -- plain / q-k-v: the rank-th 64 rows of
-                // the half's 128 columns; SwiGLU (rows [0,128) of a block are gate, [128,256) up): 64 gate rows for the leader, the
-                // matching 64 up rows for the peer, so that accumulator columns [0,64) / [64,128) are gate_j / up_j again
-                const int n0 = half < 0 ? nb * kGN + (int)rank * (kGN / 2)
-                                        : (MODE == kGemmSwiGLU ? nb * kGN + (int)rank * 128 + half * 64 : nb * kGN + half * 128 + (int)rank * 64);
+                const int n0 = half < 0 ? nb * kGN + (int)rank * (kGN / 2) : nb * kGN + half * 128 + (int)rank * 64;
                 const CUtensorMap* wmap = half < 0 ? &tm_w : &tm_wh;
                 const uint32_t bytes = half < 0 ? 2 * kStageBytes : 2 * (kABytes + kBBytes / 2);
                 for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
@@ -376,20 +372,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             if (MODE == kGemmSwiGLU) {
                 if (issuer) bulk_wait_read0();           // the previous unit's TMA store has finished reading the staging tile
                 epi_bar();
-                // full unit: gate columns [0,128), up columns [128,256), this warp converts chunks 2cg and 2cg+1 (32 columns
-                // each); half unit (tail round): gate [0,64), up [64,128), one chunk per warp
-                const int n_chunks = half < 0 ? 2 : 1;
-                const uint32_t up_off = half < 0 ? 128u : 64u;
 #pragma unroll 1
-                for (int ci = 0; ci < n_chunks; ++ci) {
-                    const int cc = half < 0 ? 2 * cg + ci : cg;
+                for (int cc = 2 * cg; cc < 2 * cg + 2; ++cc) {
                     uint32_t g[32], u[32];
                     tmem_ld32_async(acc + cc * 32, g);
-                    tmem_ld32_async(acc + up_off + cc * 32, u);
+                    tmem_ld32_async(acc + 128 + cc * 32, u);
                     tmem_ld_wait();
                     pin32(g);
                     pin32(u);
-                    if (ci == n_chunks - 1) release_acc();
+                    if (cc == 2 * cg + 1) release_acc();
                     uint32_t o[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
@@ -407,12 +398,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 fence_async_smem();
                 epi_bar();
                 if (issuer && m0 < p.M) {
-                    if (half < 0) {
-                        tma_store_2d(&tm_o, s_u32(stg), nb * 128, m0);
-                        tma_store_2d(&tm_o, s_u32(stg) + 16384, nb * 128 + 64, m0);
-                    } else {
-                        tma_store_2d(&tm_o, s_u32(stg), nb * 128 + half * 64, m0);
-                    }
+                    tma_store_2d(&tm_o, s_u32(stg), nb * 128, m0);
+                    tma_store_2d(&tm_o, s_u32(stg) + 16384, nb * 128 + 64, m0);
                     bulk_commit();
                 }
             } else if (MODE == kGemmQkvRope) {
@@ -636,11 +623,12 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     }
     const int max_clusters = num_sms / 2 > 0 ? num_sms / 2 : 1;
     const int n_tiles = p.n_mblk * p.n_nblk;
+    const bool can_split = g.mode != kGemmSwiGLU;
     int n_clusters = max_clusters;
-    if (n_tiles < max_clusters) n_clusters = 2 * n_tiles <= max_clusters ? 2 * n_tiles : n_tiles;
+    if (n_tiles < max_clusters) n_clusters = can_split && 2 * n_tiles <= max_clusters ? 2 * n_tiles : n_tiles;
     p.n_rounds = n_tiles / n_clusters;
     p.tail_tiles = n_tiles - p.n_rounds * n_clusters;
-    p.split_tail = p.tail_tiles > 0 && 2 * p.tail_tiles <= n_clusters ? 1 : 0;
+    p.split_tail = can_split && p.tail_tiles > 0 && 2 * p.tail_tiles <= n_clusters ? 1 : 0;
     const dim3 grid(2u * (unsigned)n_clusters);
     switch (g.mode) {
         case kGemmPlain: gemm_tc_kernel<kGemmPlain><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
