@@ -251,6 +251,8 @@ extern "C" int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, in
 {
     if (!qkv_bf16 || !cos || !sin) return fail(UG_ERR_NULL, "ug_rope_qk: null pointer");
     if (M < 1 || L < 1 || D % 16 != 0 || Hq < 1 || Hkv < 1 || M % L != 0) return fail(UG_ERR_SHAPE, "ug_rope_qk: bad shape");
+    if (kv_cache_bf16 && M % L != 0)
+        return fail(UG_ERR_SHAPE, "ug_qkv_rope_bf16: with a K/V cache M (%d) must be a whole number of sequences of L (%d) rows", M, L);
     if (kv_cache_bf16 && (cache_row_offset < 0 || cache_row_offset + L > cache_L))
         return fail(UG_ERR_SHAPE, "ug_rope_qk: cache window [%d, %d) outside cache_L=%d", cache_row_offset, cache_row_offset + L, cache_L);
     if (!aligned16(qkv_bf16) || !aligned16(cos) || !aligned16(sin) || !aligned16(kv_cache_bf16))
