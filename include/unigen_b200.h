@@ -200,7 +200,8 @@ int ug_qkv_rope_bf16(const void* a, const void* w_qkv, const void* bias_qkv, voi
  *   ug_groupnorm_nhwc_bf16  : y = GroupNorm(32 groups, eps)(x + in_bias) * gamma + beta, then y * sigmoid(y) when swish != 0
  *                             (common_modules.py:19-27); in_bias (nullable, bf16 [C]) = the bias of the convolution that produced
  *                             x, added here instead of in a pass of its own; x, y bf16 [B, HW, C] (may alias), C % 32 == 0,
- *                             C % 8 == 0, 256 % (C/8) == 0; workspace fp32 of ug_groupnorm_workspace_floats(B, HW, C) elements
+ *                             C % 8 == 0, 256 % (C/8) == 0; workspace fp32 of ug_groupnorm_workspace_floats(B, HW, C) elements;
+ *                             stats_ready != 0: the partial sums of x are already in the workspace (ug_bias_add_stats_nhwc_bf16)
  *   ug_bias_add_nhwc_bf16   : out = a + bias_a (+ r (+ bias_r)), bf16 [rows, C]: conv2 bias + shortcut (+ nin_shortcut bias) of a
  *                             ResnetBlock (common_modules.py:343-360) in one pass; bias_a, r, bias_r nullable; out may alias a or r
  *   ug_upsample2x_nhwc_bf16 : F.interpolate(scale_factor=2, mode="nearest") (common_modules.py:40), [B,H,W,C] -> [B,2H,2W,C]
@@ -208,7 +209,12 @@ int ug_qkv_rope_bf16(const void* a, const void* w_qkv, const void* bias_qkv, voi
 int ug_lfq_unpack_bf16(const int64_t* ids, void* z_bf16, int64_t n, int dim, void* stream);
 size_t ug_groupnorm_workspace_floats(int B, int64_t HW, int C);
 int ug_groupnorm_nhwc_bf16(const void* x_bf16, const void* in_bias_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16,
-                           float* workspace, int B, int64_t HW, int C, float eps, int swish, void* stream);
+                           float* workspace, int B, int64_t HW, int C, float eps, int swish, int stats_ready, void* stream);
+/* ug_bias_add_nhwc_bf16 on [B, HW, C] that also leaves the GroupNorm partial sums of `out` in `workspace`; the next
+ * ug_groupnorm_nhwc_bf16 on `out` with the same workspace may pass stats_ready = 1 and skip its statistics pass (the partial sums
+ * are bit-identical to the ones that pass would compute).  Shape limits of ug_groupnorm_nhwc_bf16. */
+int ug_bias_add_stats_nhwc_bf16(const void* a_bf16, const void* bias_a_bf16, const void* r_bf16, const void* bias_r_bf16, void* out_bf16,
+                                float* workspace, int B, int64_t HW, int C, void* stream);
 int ug_bias_add_nhwc_bf16(const void* a_bf16, const void* bias_a_bf16, const void* r_bf16, const void* bias_r_bf16, void* out_bf16,
                           int64_t rows, int C, void* stream);
 int ug_upsample2x_nhwc_bf16(const void* x_bf16, void* y_bf16, int B, int H, int W, int C, void* stream);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("UNIGEN_B200_LIB") or os.path.join(_HERE, "csrc", "lib
 UG_ABI_VERSION = 1
 SYMBOLS = (
     "ug_abi_version", "ug_last_error", "ug_decode_step_workspace_bytes", "ug_decode_step_bf16",
-    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_omni_attention_rows_bf16", "ug_debug_set_rowsum_out", "ug_debug_set_force_full_race", "ug_debug_set_decode_mode", "ug_debug_set_decode_stats", "ug_debug_set_attn_dump", "ug_add_rmsnorm", "ug_rope_qk", "ug_swiglu", "ug_embed_rows", "ug_gemm_bf16", "ug_qkv_rope_bf16", "ug_lfq_unpack_bf16", "ug_groupnorm_workspace_floats", "ug_groupnorm_nhwc_bf16", "ug_bias_add_nhwc_bf16", "ug_cfg_mix_bf16",
+    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_omni_attention_rows_bf16", "ug_debug_set_rowsum_out", "ug_debug_set_force_full_race", "ug_debug_set_decode_mode", "ug_debug_set_decode_stats", "ug_debug_set_attn_dump", "ug_add_rmsnorm", "ug_rope_qk", "ug_swiglu", "ug_embed_rows", "ug_gemm_bf16", "ug_qkv_rope_bf16", "ug_lfq_unpack_bf16", "ug_groupnorm_workspace_floats", "ug_groupnorm_nhwc_bf16", "ug_bias_add_nhwc_bf16", "ug_bias_add_stats_nhwc_bf16", "ug_cfg_mix_bf16",
     "ug_upsample2x_nhwc_bf16",
 )
 
@@ -101,7 +101,10 @@ def lib() -> ctypes.CDLL:
     L.ug_groupnorm_workspace_floats.argtypes = [c.c_int, c.c_int64, c.c_int]
     L.ug_groupnorm_nhwc_bf16.restype = c.c_int
     L.ug_groupnorm_nhwc_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int64,
-                                         c.c_int, c.c_float, c.c_int, c.c_void_p]
+                                         c.c_int, c.c_float, c.c_int, c.c_int, c.c_void_p]
+    L.ug_bias_add_stats_nhwc_bf16.restype = c.c_int
+    L.ug_bias_add_stats_nhwc_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int64,
+                                              c.c_int, c.c_void_p]
     L.ug_bias_add_nhwc_bf16.restype = c.c_int
     L.ug_bias_add_nhwc_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_void_p]
     L.ug_upsample2x_nhwc_bf16.restype = c.c_int

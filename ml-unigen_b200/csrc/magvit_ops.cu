@@ -45,8 +45,14 @@ __global__ void __launch_bounds__(256) lfq_unpack_kernel(const int64_t* __restri
 
 // grid (chunks, B); block kGnThreads.  Thread t owns vector slot t % (C/8) (8 consecutive channels) of the rows
 // t / (C/8) + k * (kGnThreads / (C/8)) of its chunk.  Requires C % 8 == 0 and kGnThreads % (C/8) == 0.
+// kFused: the pass also PRODUCES the tensor the statistics are taken of: out = x + in_bias (+ r (+ bias_r)) is rounded to bf16,
+// stored, and the sums are taken over the rounded values -- the same values, thread mapping and summation order as the plain
+// statistics pass over `out` would use, so the partial sums are bit-identical to it and the following GroupNorm skips its own
+// statistics pass (the residual add at the end of a ResnetBlock feeds norm1 of the next one).
+template <bool kFused>
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ in_bias,
-                                                              float* __restrict__ partial, int64_t HW, int C)
+                                                              const uint4* __restrict__ r_in, const __nv_bfloat16* __restrict__ bias_r,
+                                                              uint4* __restrict__ out, float* __restrict__ partial, int64_t HW, int C)
 {
     __shared__ float s_part[kGnThreads * 8], q_part[kGnThreads * 8];
     const int vecs = C / 8;
@@ -58,17 +64,39 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __res
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.0f; q[e] = 0.0f; }
     const uint4* xb = x + (int64_t)b * HW * vecs;
-    float ib[8];                                   // per-channel bias of the producing convolution (added here instead of in a pass of its own)
+    float ib[8], rb[8];                            // per-channel bias of the producing convolution (added here instead of in a pass of its own)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) ib[e] = in_bias ? __bfloat162float(in_bias[slot * 8 + e]) : 0.0f;
+    for (int e = 0; e < 8; ++e) {
+        ib[e] = in_bias ? __bfloat162float(in_bias[slot * 8 + e]) : 0.0f;
+        rb[e] = (kFused && bias_r) ? __bfloat162float(bias_r[slot * 8 + e]) : 0.0f;
+    }
     for (int64_t r = r_begin + row0; r < r_end; r += rstep) {
+        const int64_t idx = (int64_t)b * HW * vecs + r * vecs + slot;
         const uint4 v = xb[r * vecs + slot];
-        const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
+        float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
+        if (kFused) {
+            if (in_bias) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float t = f[e] + ib[e];
-            s[e] += t;
-            q[e] = fmaf(t, t, q[e]);
+                for (int e = 0; e < 8; ++e) f[e] += ib[e];
+            }
+            if (r_in) {
+                const uint4 vr = r_in[idx];
+                const float g[8] = {bf_lo(vr.x), bf_hi(vr.x), bf_lo(vr.y), bf_hi(vr.y), bf_lo(vr.z), bf_hi(vr.z), bf_lo(vr.w), bf_hi(vr.w)};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += g[e] + rb[e];
+            }
+            const uint4 o = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+            out[idx] = o;
+            const float h[8] = {bf_lo(o.x), bf_hi(o.x), bf_lo(o.y), bf_hi(o.y), bf_lo(o.z), bf_hi(o.z), bf_lo(o.w), bf_hi(o.w)};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s[e] += h[e]; q[e] = fmaf(h[e], h[e], q[e]); }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float t = f[e] + ib[e];
+                s[e] += t;
+                q[e] = fmaf(t, t, q[e]);
+            }
         }
     }
 #pragma unroll
@@ -200,15 +228,28 @@ size_t groupnorm_workspace_floats(int B, int64_t HW, int C)
     return (size_t)B * (size_t)chunks * kGroups * 2 + (size_t)B * kGroups * 2;
 }
 
-cudaError_t launch_groupnorm_nhwc(const void* x, const void* in_bias, const void* gamma, const void* beta, void* y, float* workspace,
-                                  int B, int64_t HW, int C, float eps, int swish, cudaStream_t stream)
+cudaError_t launch_bias_add_stats_nhwc(const void* a, const void* bias_a, const void* r, const void* bias_r, void* out, float* workspace,
+                                       int B, int64_t HW, int C, cudaStream_t stream)
 {
     if (B < 1 || HW < 1 || C % kGroups != 0 || C % 8 != 0 || kGnThreads % (C / 8) != 0) return cudaErrorInvalidValue;
     const int chunks = (int)((HW + kGnRowsPerBlock - 1) / kGnRowsPerBlock);
+    gn_stats_kernel<true><<<dim3((unsigned)chunks, (unsigned)B), kGnThreads, 0, stream>>>(
+        reinterpret_cast<const uint4*>(a), reinterpret_cast<const __nv_bfloat16*>(bias_a), reinterpret_cast<const uint4*>(r),
+        reinterpret_cast<const __nv_bfloat16*>(bias_r), reinterpret_cast<uint4*>(out), workspace, HW, C);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_groupnorm_nhwc(const void* x, const void* in_bias, const void* gamma, const void* beta, void* y, float* workspace,
+                                  int B, int64_t HW, int C, float eps, int swish, int stats_ready, cudaStream_t stream)
+{
+    if (B < 1 || HW < 1 || C % kGroups != 0 || C % 8 != 0 || kGnThreads % (C / 8) != 0) return cudaErrorInvalidValue;
+    if (stats_ready && in_bias) return cudaErrorInvalidValue;        // the producer's sums are those of x itself
+    const int chunks = (int)((HW + kGnRowsPerBlock - 1) / kGnRowsPerBlock);
     float* partial = workspace;
     float* stats = workspace + (size_t)B * chunks * kGroups * 2;
-    gn_stats_kernel<<<dim3((unsigned)chunks, (unsigned)B), kGnThreads, 0, stream>>>(
-        reinterpret_cast<const uint4*>(x), reinterpret_cast<const __nv_bfloat16*>(in_bias), partial, HW, C);
+    if (!stats_ready)
+        gn_stats_kernel<false><<<dim3((unsigned)chunks, (unsigned)B), kGnThreads, 0, stream>>>(
+            reinterpret_cast<const uint4*>(x), reinterpret_cast<const __nv_bfloat16*>(in_bias), nullptr, nullptr, nullptr, partial, HW, C);
     gn_finalize_kernel<<<B, kGroups, 0, stream>>>(partial, stats, chunks, 1.0 / ((double)HW * (C / kGroups)), eps);
     gn_apply_kernel<<<grid_for((int64_t)B * HW * (C / 8), 256), 256, 0, stream>>>(
         reinterpret_cast<const uint4*>(x), reinterpret_cast<const __nv_bfloat16*>(in_bias), reinterpret_cast<const __nv_bfloat16*>(gamma),

@@ -13,7 +13,12 @@ cudaError_t launch_lfq_unpack(const int64_t* ids, void* z_bf16, int64_t n, int d
 size_t groupnorm_workspace_floats(int B, int64_t HW, int C);
 // in_bias (nullable, bf16 [C]) is added to x first: the bias of the convolution that produced x
 cudaError_t launch_groupnorm_nhwc(const void* x_bf16, const void* in_bias_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16,
-                                  float* workspace, int B, int64_t HW, int C, float eps, int swish, cudaStream_t stream);
+                                  float* workspace, int B, int64_t HW, int C, float eps, int swish, int stats_ready, cudaStream_t stream);
+
+// bias_add that also leaves the GroupNorm partial sums of `out` in `workspace` (same layout as the statistics pass): the next
+// launch_groupnorm_nhwc on `out` may then be called with stats_ready = 1.  Same shape limits as launch_groupnorm_nhwc.
+cudaError_t launch_bias_add_stats_nhwc(const void* a_bf16, const void* bias_a_bf16, const void* r_bf16, const void* bias_r_bf16, void* out_bf16,
+                                       float* workspace, int B, int64_t HW, int C, cudaStream_t stream);
 
 // out = a + bias_a[c] (+ r (+ bias_r[c])), bf16 [rows, C]; bias_a, r, bias_r nullable; out may alias a or r
 cudaError_t launch_bias_add_nhwc(const void* a_bf16, const void* bias_a_bf16, const void* r_bf16, const void* bias_r_bf16, void* out_bf16,

@@ -367,14 +367,30 @@ extern "C" int ug_bias_add_nhwc_bf16(const void* a_bf16, const void* bias_a_bf16
     return UG_OK;
 }
 
+extern "C" int ug_bias_add_stats_nhwc_bf16(const void* a_bf16, const void* bias_a_bf16, const void* r_bf16, const void* bias_r_bf16, void* out_bf16,
+                                           float* workspace, int B, int64_t HW, int C, void* stream)
+{
+    if (!a_bf16 || !out_bf16 || !workspace) return fail(UG_ERR_NULL, "ug_bias_add_stats_nhwc_bf16: null pointer");
+    if (bias_r_bf16 && !r_bf16) return fail(UG_ERR_ARG, "ug_bias_add_stats_nhwc_bf16: bias_r without r");
+    if (B < 1 || HW < 1 || C < 32 || C % 32 || C % 8 || 256 % (C / 8))
+        return fail(UG_ERR_SHAPE, "ug_bias_add_stats_nhwc_bf16: need C %% 32 == 0 and 256 %% (C/8) == 0 (C=%d)", C);
+    if (!aligned16(a_bf16) || !aligned16(out_bf16) || (r_bf16 && !aligned16(r_bf16)))
+        return fail(UG_ERR_ALIGN, "ug_bias_add_stats_nhwc_bf16: pointers must be 16-byte aligned");
+    cudaError_t e = ugk::launch_bias_add_stats_nhwc(a_bf16, bias_a_bf16, r_bf16, bias_r_bf16, out_bf16, workspace, B, HW, C,
+                                                    static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_bias_add_stats_nhwc_bf16 launch");
+    return UG_OK;
+}
+
 extern "C" int ug_groupnorm_nhwc_bf16(const void* x_bf16, const void* in_bias_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16,
-                                      float* workspace, int B, int64_t HW, int C, float eps, int swish, void* stream)
+                                      float* workspace, int B, int64_t HW, int C, float eps, int swish, int stats_ready, void* stream)
 {
     if (!x_bf16 || !gamma_bf16 || !beta_bf16 || !y_bf16 || !workspace) return fail(UG_ERR_NULL, "ug_groupnorm_nhwc_bf16: null pointer");
     if (B < 1 || HW < 1 || C < 32 || C % 32 || C % 8 || 256 % (C / 8))
         return fail(UG_ERR_SHAPE, "ug_groupnorm_nhwc_bf16: need C %% 32 == 0 and 256 %% (C/8) == 0 (C=%d)", C);
     if (!aligned16(x_bf16) || !aligned16(y_bf16)) return fail(UG_ERR_ALIGN, "ug_groupnorm_nhwc_bf16: x and y must be 16-byte aligned");
-    cudaError_t e = ugk::launch_groupnorm_nhwc(x_bf16, in_bias_bf16, gamma_bf16, beta_bf16, y_bf16, workspace, B, HW, C, eps, swish,
+    if (stats_ready && in_bias_bf16) return fail(UG_ERR_ARG, "ug_groupnorm_nhwc_bf16: stats_ready excludes in_bias");
+    cudaError_t e = ugk::launch_groupnorm_nhwc(x_bf16, in_bias_bf16, gamma_bf16, beta_bf16, y_bf16, workspace, B, HW, C, eps, swish, stats_ready,
                                                static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "ug_groupnorm_nhwc_bf16 launch");
     return UG_OK;

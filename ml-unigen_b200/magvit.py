@@ -48,9 +48,11 @@ _gn_ws = _GroupNormWorkspace()
 
 
 def groupnorm_swish(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6, swish: bool = True,
-                    out: Optional[torch.Tensor] = None, in_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    out: Optional[torch.Tensor] = None, in_bias: Optional[torch.Tensor] = None,
+                    stats_ready: bool = False) -> torch.Tensor:
     """x bf16 NHWC [B,H,W,C] (contiguous) -> GroupNorm(32, eps)(x + in_bias)*gamma+beta, then y*sigmoid(y) if `swish`.
-    `in_bias` (bf16 [C]): the bias of the convolution that produced x, folded into this pass."""
+    `in_bias` (bf16 [C]): the bias of the convolution that produced x, folded into this pass.  `stats_ready`: x was just
+    produced by `bias_add(..., emit_stats=True)`, whose partial sums are still in the shared workspace: no statistics pass."""
     ops._need_cuda(x, gamma, beta, in_bias)
     B, H, W, C = x.shape
     if x.dtype != torch.bfloat16 or not x.is_contiguous() or gamma.dtype != torch.bfloat16 or beta.dtype != torch.bfloat16:
@@ -61,13 +63,15 @@ def groupnorm_swish(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ep
     if in_bias is not None and (in_bias.dtype != torch.bfloat16 or in_bias.numel() != C or not in_bias.is_contiguous()):
         raise ValueError("in_bias must be contiguous bf16 [C]")
     _lib.check(_lib.lib().ug_groupnorm_nhwc_bf16(ops._ptr(x), ops._ptr(in_bias), ops._ptr(gamma), ops._ptr(beta), ops._ptr(out), ops._ptr(ws),
-                                                 B, H * W, C, float(eps), 1 if swish else 0, ops._stream()))
+                                                 B, H * W, C, float(eps), 1 if swish else 0, 1 if stats_ready else 0, ops._stream()))
     return out
 
 
 def bias_add(a: torch.Tensor, bias_a: Optional[torch.Tensor], r: Optional[torch.Tensor] = None,
-             bias_r: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = a + bias_a (+ r (+ bias_r)) on bf16 NHWC tensors [.., C] in one pass (default: in place on `a`)."""
+             bias_r: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, emit_stats: bool = False) -> torch.Tensor:
+    """out = a + bias_a (+ r (+ bias_r)) on bf16 NHWC tensors [.., C] in one pass (default: in place on `a`).  With
+    `emit_stats` (a must be [B,H,W,C]) the pass also leaves the GroupNorm partial sums of `out` in the shared workspace for
+    an immediately following `groupnorm_swish(out, ..., stats_ready=True)`."""
     ops._need_cuda(a, bias_a, r, bias_r)
     C = a.shape[-1]
     if a.dtype != torch.bfloat16 or not a.is_contiguous() or (r is not None and (r.shape != a.shape or not r.is_contiguous()
@@ -78,6 +82,12 @@ def bias_add(a: torch.Tensor, bias_a: Optional[torch.Tensor], r: Optional[torch.
             raise ValueError("biases must be contiguous bf16 [C]")
     if out is None:
         out = a
+    if emit_stats:
+        B, H, W, _ = a.shape
+        ws = _gn_ws.get(B, H * W, C, a.device)
+        _lib.check(_lib.lib().ug_bias_add_stats_nhwc_bf16(ops._ptr(a), ops._ptr(bias_a), ops._ptr(r), ops._ptr(bias_r), ops._ptr(out),
+                                                          ops._ptr(ws), B, H * W, C, ops._stream()))
+        return out
     _lib.check(_lib.lib().ug_bias_add_nhwc_bf16(ops._ptr(a), ops._ptr(bias_a), ops._ptr(r), ops._ptr(bias_r), ops._ptr(out),
                                                 a.numel() // C, C, ops._stream()))
     return out
@@ -165,16 +175,18 @@ class MagvitV2DecoderB200:
         return cls(w, num_res_blocks, device, z_channels)
 
     # ---------------------------------------------------------------------------------------------
-    def _res(self, p: str, x: torch.Tensor) -> torch.Tensor:
+    def _res(self, p: str, x: torch.Tensor, x_stats_ready: bool = False, emit_stats: bool = False) -> torch.Tensor:
+        """ResnetBlock.  `x_stats_ready`: x comes from a block that ran with `emit_stats` (its residual add already summed
+        x for this block's norm1); `emit_stats`: the next consumer of the result is a GroupNorm over the same tensor."""
         w = self.w
-        h = groupnorm_swish(x, w[p + "norm1.weight"], w[p + "norm1.bias"])
+        h = groupnorm_swish(x, w[p + "norm1.weight"], w[p + "norm1.bias"], stats_ready=x_stats_ready)
         h = _conv(h, w[p + "conv1.weight"], None, 1)
         h = groupnorm_swish(h, w[p + "norm2.weight"], w[p + "norm2.bias"], out=h, in_bias=w[p + "conv1.bias"])
         h = _conv(h, w[p + "conv2.weight"], None, 1)
         if p + "nin_shortcut.weight" in w:
             xs = _conv(x, w[p + "nin_shortcut.weight"], None, 0)
-            return bias_add(h, w[p + "conv2.bias"], xs, w[p + "nin_shortcut.bias"])
-        return bias_add(h, w[p + "conv2.bias"], x)
+            return bias_add(h, w[p + "conv2.bias"], xs, w[p + "nin_shortcut.bias"], emit_stats=emit_stats)
+        return bias_add(h, w[p + "conv2.bias"], x, emit_stats=emit_stats)
 
     def _attn(self, p: str, x: torch.Tensor) -> torch.Tensor:
         w = self.w
@@ -199,12 +211,18 @@ class MagvitV2DecoderB200:
         h = self._res("mid.block_1.", h)
         h = self._attn("mid.attn_1.", h)
         h = self._res("mid.block_2.", h)
+        ready = False                      # h was produced by a block that left its GroupNorm partial sums in the workspace
         for lvl in reversed(range(len(self.num_res_blocks))):
-            for i in range(self.num_res_blocks[lvl]):
-                h = self._res(f"up.{lvl}.block.{i}.", h)
+            n_blk = self.num_res_blocks[lvl]
+            for i in range(n_blk):
+                # the result feeds a GroupNorm directly (next block's norm1, or norm_out) unless an upsample follows
+                emit = i + 1 < n_blk or lvl == 0
+                h = self._res(f"up.{lvl}.block.{i}.", h, x_stats_ready=ready, emit_stats=emit)
+                ready = emit
             if lvl != 0:
                 h = upsample2x(h)
-                h = bias_add(_conv(h, w[f"up.{lvl}.upsample.conv.weight"], None, 1), w[f"up.{lvl}.upsample.conv.bias"])
-        h = groupnorm_swish(h, w["norm_out.weight"], w["norm_out.bias"], out=h)
+                h = bias_add(_conv(h, w[f"up.{lvl}.upsample.conv.weight"], None, 1), w[f"up.{lvl}.upsample.conv.bias"], emit_stats=True)
+                ready = True                 # ... and feeds norm1 of the next level's first block
+        h = groupnorm_swish(h, w["norm_out.weight"], w["norm_out.bias"], out=h, stats_ready=ready)
         h = _conv(h, w["conv_out.weight"], w["conv_out.bias"], 1)
         return h.permute(0, 3, 1, 2).float()

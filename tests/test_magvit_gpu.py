@@ -75,6 +75,26 @@ def test_groupnorm_input_bias_and_bias_add(dev):
     assert torch.equal(magvit.bias_add(x.clone(), b1), (x.float() + b1.float()).bfloat16())
 
 
+def test_bias_add_with_fused_groupnorm_statistics(dev):
+    """bias_add(..., emit_stats=True) + groupnorm_swish(..., stats_ready=True) == bias_add + groupnorm_swish, bit for bit
+    (same values, same thread mapping, same summation order in the fused statistics)."""
+    from ml_unigen_b200 import magvit
+    g = torch.Generator(device=dev).manual_seed(3)
+    for B, H, W, C in ((2, 40, 24, 128), (1, 33, 17, 256), (3, 16, 16, 32), (2, 64, 64, 512)):
+        a = torch.randn(B, H, W, C, device=dev, generator=g).bfloat16()
+        r = torch.randn(B, H, W, C, device=dev, generator=g).bfloat16()
+        b1 = torch.randn(C, device=dev, generator=g).bfloat16()
+        b2 = torch.randn(C, device=dev, generator=g).bfloat16()
+        gamma = (1 + 0.2 * torch.randn(C, device=dev, generator=g)).bfloat16()
+        beta = (0.1 * torch.randn(C, device=dev, generator=g)).bfloat16()
+        for rr, bb in ((r, b2), (r, None), (None, None)):
+            plain = magvit.bias_add(a.clone(), b1, rr, bb)
+            y_plain = magvit.groupnorm_swish(plain, gamma, beta)
+            fused = magvit.bias_add(a.clone(), b1, rr, bb, emit_stats=True)
+            y_fused = magvit.groupnorm_swish(fused, gamma, beta, stats_ready=True)
+            assert torch.equal(fused, plain) and torch.equal(y_fused, y_plain)
+
+
 def test_upsample2x_exact(dev):
     from ml_unigen_b200 import magvit
     x = torch.randn(2, 5, 7, 64, device=dev).bfloat16()
