@@ -124,7 +124,7 @@ int ug_cfg_mix_bf16(void* cond_logits_inout, const void* uncond_logits, float gu
  *   k,v bf16 [B,L,Hkv,D]  (kv_stride_b, kv_stride_l, kv_stride_h)
  *   out bf16 [B,L,Hq,D]   (o_stride_b, o_stride_l, o_stride_h)
  *   pad_len, soi_idx int32 [B] on the device
- * Supported: D = 128, Hq % Hkv == 0, all strides multiples of 8 elements, 16-byte aligned bases.
+ * Supported: D = 128, Hq % Hkv == 0, L <= 4096, all strides multiples of 8 elements, 16-byte aligned bases.
  */
 int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* out,
                            const int32_t* pad_len, const int32_t* soi_idx,

@@ -172,9 +172,9 @@ int ug_omni_attention_rows_bf16(const void* q, const void* k, const void* v, voi
                                 void* stream)
 {
     if (!q || !k || !v || !out || !pad_len || !soi_idx) return fail(UG_ERR_NULL, "ug_omni_attention_bf16: null pointer");
-    if (D != 128 || Hkv < 1 || Hq % Hkv != 0 || B < 1 || L < 1 || Lq < 1 || q_row_offset < 0 || q_row_offset + Lq > L)
-        return fail(UG_ERR_SHAPE, "ug_omni_attention_bf16: B=%d L=%d Lq=%d q0=%d Hq=%d Hkv=%d D=%d unsupported (D=128, Hq%%Hkv==0, q0+Lq<=L)",
-                    B, L, Lq, q_row_offset, Hq, Hkv, D);
+    if (D != 128 || Hkv < 1 || Hq % Hkv != 0 || B < 1 || L < 1 || L > 4096 || Lq < 1 || q_row_offset < 0 || q_row_offset + Lq > L)
+        return fail(UG_ERR_SHAPE, "ug_omni_attention_bf16: B=%d L=%d Lq=%d q0=%d Hq=%d Hkv=%d D=%d unsupported (D=128, Hq%%Hkv==0, "
+                    "L<=4096: 32 kv tiles per row of work masks, q0+Lq<=L)", B, L, Lq, q_row_offset, Hq, Hkv, D);
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out) ||
         ((q_stride_b | q_stride_l | q_stride_h | kv_stride_b | kv_stride_l | kv_stride_h | o_stride_b | o_stride_l | o_stride_h) & 7))
         return fail(UG_ERR_ALIGN, "ug_omni_attention_bf16: bases must be 16-byte aligned and strides multiples of 8 elements");

@@ -139,6 +139,27 @@ def test_rejects_unsupported_shapes(dev):
                            torch.zeros(1, dtype=torch.int32, device=dev), 1.0)
 
 
+def test_rejects_sequences_longer_than_the_work_masks(dev):
+    from ml_unigen_b200 import ops, _lib
+    q = torch.zeros(1, 4100, 2, 128, dtype=torch.bfloat16, device=dev)
+    z = torch.zeros(1, dtype=torch.int32, device=dev)
+    with pytest.raises(_lib.UnigenB200Error):
+        ops.omni_attention(q, q, q, z, z, 1.0)
+
+
+def test_longest_supported_sequence(dev):
+    """L = 4096 (32 kv tiles: the last bit of the per-tile work masks) and L = 4000 (end-aligned tiles), window pass."""
+    from ml_unigen_b200 import ops
+    for L, P, S in ((4096, 5, 700), (4000, 200, 300)):
+        q, k, v = _mk(1, L, 2, 1, 128, seed=L, dev=dev)
+        Pt = torch.tensor([P], dtype=torch.int32, device=dev)
+        St = torch.tensor([S], dtype=torch.int32, device=dev)
+        s0 = L - 300
+        part = ops.omni_attention(q[:, s0:], k, v, Pt, St, 128 ** -0.5, q_offset=s0)
+        ref = BO.attention_ref(q, k, v, Pt, St, 128 ** -0.5)[:, s0:]
+        _check(part, ref, tag=f"L={L}")
+
+
 def test_query_row_window_equals_full_attention_rows(dev):
     """ug_omni_attention_rows_bf16 (image-block rows only, the prefix K/V reuse pass) returns exactly the rows the
     full pass returns -- each query row sees the same kv tiles in the same order."""
