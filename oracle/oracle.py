@@ -6,7 +6,7 @@ restatement of the host-side schedule arithmetic (models/sampling.py:49-88,
 models/unigen.py:425-444).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
-may import this module.  Nothing under ml-unigen_b200/ does.
+may import this module.  Nothing under ml_unigen_b200/ does.
 """
 from __future__ import annotations
 

@@ -1,4 +1,4 @@
-// Host build of ml-unigen_b200/csrc/ug_math.cuh: the kernel's arithmetic source, executed on
+// Host build of ml_unigen_b200/csrc/ug_math.cuh: the kernel's arithmetic source, executed on
 // the CPU so tests can compare it bit for bit with oracle/decode_step_oracle.c without a GPU.
 #include "ug_math.cuh"
 extern "C" {

@@ -1,4 +1,4 @@
-"""CPU: the kernel's arithmetic header (ml-unigen_b200/csrc/ug_math.cuh) compiled for the host
+"""CPU: the kernel's arithmetic header (ml_unigen_b200/csrc/ug_math.cuh) compiled for the host
 must agree bit for bit with the C oracle: exp (both scaling variants), log, Philox noise
 streams, confidence, bf16 CFG mix.  This is what makes GPU-vs-oracle equality a by-construction
 property rather than a statistical one."""
@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def hostlib(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("hostmath") / "libug_hostmath.so")
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "--shared", "-Xcompiler", "-fPIC,-ffp-contract=off",
-                           "-I" + os.path.join(ROOT, "ml-unigen_b200", "csrc"),
+                           "-I" + os.path.join(ROOT, "ml_unigen_b200", "csrc"),
                            os.path.join(ROOT, "tests", "host_math_check.cu"), "-o", out])
     L = ctypes.CDLL(out)
     for name in ("ugk_host_expf_exact", "ugk_host_expf_fast", "ugk_host_logf"):

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Builds experiment variants of libunigen_b200.so (different -D switches of gemm_tc.cu) into build/exp/.
 set -e
-cd "$(dirname "$0")/../ml-unigen_b200/csrc"
+cd "$(dirname "$0")/../ml_unigen_b200/csrc"
 mkdir -p ../../build/exp
 python build.py > /dev/null
 for v in "$@"; do

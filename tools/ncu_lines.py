@@ -1,6 +1,6 @@
 """Per-source-line view of an .ncu-rep: joins the SASS page of the report (address, stall samples, executed
 instructions) with `nvdisasm -g` line information of the kernel's cubin.
-Usage: python tools/ncu_lines.py gpurun_out/prof.ncu-rep ml-unigen_b200/csrc/decode_fast.o decode_fast_kernelILi32 [top]"""
+Usage: python tools/ncu_lines.py gpurun_out/prof.ncu-rep ml_unigen_b200/csrc/decode_fast.o decode_fast_kernelILi32 [top]"""
 import collections
 import csv
 import glob
