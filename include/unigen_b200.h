@@ -8,6 +8,9 @@
  * throws, or exits.  All work is enqueued on `stream` (a cudaStream_t passed as void*), so a
  * T-step generation loop can be captured in a CUDA graph.
  *
+ * There is no global or thread-local switch that alters the behaviour of a call: everything a call does is determined by
+ * its arguments (test instrumentation lives in unigen_b200_test.h behind the ugt_ prefix, passed explicitly per call).
+ *
  * Return value: 0 on success; negative UG_ERR_* for rejected arguments; positive = the
  * cudaError_t reported by the launch.  ug_last_error() returns a thread-local message.
  *
@@ -34,7 +37,7 @@
 extern "C" {
 #endif
 
-#define UG_ABI_VERSION 1
+#define UG_ABI_VERSION 2
 
 enum {
     UG_OK = 0,
@@ -96,18 +99,6 @@ int ug_export_noise(uint64_t philox_seed, uint64_t philox_offset, int64_t batch_
                     int B, int N, int V, float* q_out /* [B,N,V] or NULL */, float* u_out /* [B,N] or NULL */,
                     void* stream);
 
-/* test hook: softmax denominators of subsequent decode steps of this thread (float [B,N]; NULL = off) */
-void ug_debug_set_rowsum_out(float* rowsum_out);
-/* test hook, bits: 1 = evaluate every element of every row of the race exactly (the e^-16 fallback); 2 = exact
- * evaluation of the candidate lists on every row; 4 = exact confidence for every token of the mask selection */
-void ug_debug_set_force_full_race(int on);
-/* test hook: 0 = automatic (certified fast kernel when q_noise == NULL, uncond_logits == NULL and V <= 8192),
- * 1 = always the exact-arithmetic kernel.  Both kernels return the same ids and masks. */
-void ug_debug_set_decode_mode(int mode);
-/* test hook: device uint32[8] counters of the fast kernel's exact paths -- [0] rows whose candidates were evaluated
- * exactly, [1] rows evaluated exhaustively, [2] mask selections with an undecided band, [3] rows replayed for it, [4..7] reasons of [1] (degenerate row, bound not reached, list A / B overflow) */
-void ug_debug_set_decode_stats(unsigned* counters);
-
 /* Classifier-free guidance as a pass of its own, in place on the conditional logits (models/unigen.py:410 under autocast, op by op
  * in bf16): cond[i] = bf16(bf16(scale * bf16(cond[i] - uncond[i])) + uncond[i]) for n bf16 elements (n % 8 == 0) -- exactly the
  * values ug_decode_step_bf16 forms inline when it is given uncond_logits.  The result is bf16 again, so a following
@@ -147,23 +138,27 @@ int ug_omni_attention_rows_bf16(const void* q, const void* k, const void* v, voi
                                 void* stream);
 
 /* ---- row-wise kernels of the Qwen2 decoder layer (transformers models/qwen2/modeling_qwen2.py) ------------
- * The GEMMs around them stay on cuBLAS in this round; these four replace the
- * ATen elementwise chains of Qwen2RMSNorm (+ residual add), apply_rotary_pos_emb, Qwen2MLP's
+ * These four replace the ATen elementwise chains of Qwen2RMSNorm (+ residual add), apply_rotary_pos_emb, Qwen2MLP's
  * act_fn(gate)*up and embed_tokens (models/unigen.py:370, 452).
  *   ug_add_rmsnorm : x fp32 [M,H] (+= delta bf16 [M,H] if non-NULL, written back); out bf16 [M,H] =
- *                    weight * x * rsqrt(mean(x^2) + eps).  H % 256 == 0, H <= 8192.
+ *                    weight * x * rsqrt(mean(x^2) + eps).  H = 256 k, k in 1..8, 12, 16, ..., 32.  (Since round 2 the layer loop
+ *                    no longer launches it: the residual add and the norm are GEMM epilogues; it remains as the unfused
+ *                    yardstick of those epilogues and for callers that need the normalised activations themselves.)
  *   ug_rope_qk     : in-place rotate_half RoPE on the q and k heads of qkv bf16 [M,(Hq+2Hkv)*D];
  *                    position = m % L; cos/sin fp32 [L, D/2].  With kv_cache (bf16 [B, cache_L, 2, Hkv, D]) the rotated
  *                    k and the v of row m are also written to cache row cache_row_offset + m % L of batch m / L.
  *   ug_swiglu      : act bf16 [M,I] = silu(g) * u, gate_up bf16 [M,2I] = [g | u].
- *   ug_embed_rows  : x fp32 [M,H] = table bf16 [vocab,H][tokens[m]].
+ *   ug_embed_rows  : x fp32 [M,H] = table bf16 [vocab,H][tokens[m]] (ids outside [0, vocab) are clamped for memory safety; the
+ *                    host validates them).  With xb_bf16 / ss (both or neither, H % 256 == 0) the same launch also writes
+ *                    xb = bf16(x) and ss fp32 [M, H/128] = per-128-column sums of x^2: the operands of the norm-folded GEMMs below.
  */
 int ug_add_rmsnorm(float* x, const void* delta_bf16, const void* weight_bf16, void* out_bf16,
                    int64_t M, int H, float eps, void* stream);
 int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, int64_t M, int L, int Hq, int Hkv, int D,
                void* kv_cache_bf16 /* nullable */, int cache_L, int cache_row_offset, void* stream);
 int ug_swiglu(const void* gate_up_bf16, void* act_bf16, int64_t M, int I, void* stream);
-int ug_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64_t M, int H, int64_t vocab, void* stream);
+int ug_embed_rows(float* x, void* xb_bf16 /* nullable */, float* ss /* nullable */, const void* table_bf16, const int64_t* tokens,
+                  int64_t M, int H, int64_t vocab, void* stream);
 
 /* ---- linear layers on tcgen05 with fused epilogues -------------------------------
  * Replaces torch.nn.functional.linear + the elementwise op that follows it in transformers' Qwen2MLP /
@@ -176,11 +171,28 @@ int ug_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64
  *                         w[256 j + i] = Wg[128 j + i], w[256 j + 128 + i] = Wu[128 j + i], i < 128 (`pack_gate_up`
  *                         in ml_unigen_b200.ops does this once at load time); bias must be NULL
  * Supported: N % 256 == 0, K % 64 == 0, strides multiples of 8 elements, 16-byte aligned bases; fp32 accumulation.
+ *
+ * RMSNorm folding (row_ss != NULL; also ug_qkv_rope_bf16).  Qwen2RMSNorm (input_layernorm / post_attention_layernorm / norm)
+ * commutes with the linear layer that follows it: (g * x / rms(x)) W^T = (1 / rms(x)) * (x (W diag g)^T).  The caller folds the
+ * gain g into the columns of w once at load time, passes a = bf16(x) and row_ss = fp32 [M, ss_parts] partial sums of squares of
+ * the rows of the fp32 residual stream x (as ug_gemm_residual_bf16 / ug_embed_rows leave them); the epilogue multiplies row m of
+ * the fp32 accumulator by rsqrt(sum_p row_ss[m,p] / K + rms_eps) before bias / rounding (partial sums added in index order).
+ * The separate add + RMSNorm pass over HBM (ug_add_rmsnorm) disappears from the layer.
  */
 #define UG_GEMM_PLAIN 0
 #define UG_GEMM_SWIGLU 1
 int ug_gemm_bf16(const void* a, const void* w, const void* bias, void* out, int M, int N, int K,
-                 int64_t lda, int64_t ldw, int64_t ldo, int mode, void* stream);
+                 int64_t lda, int64_t ldw, int64_t ldo, int mode,
+                 const float* row_ss /* nullable */, int ss_parts, float rms_eps, void* stream);
+
+/* o_proj / down_proj of a Qwen2DecoderLayer together with the residual add that follows them and the statistics of the next
+ * RMSNorm, in the epilogue of the same launch (reached from apple/ml-unigen models/unigen.py:260-266):
+ *     x_inout fp32 [M,N] += bf16(a w^T)     (the linear output rounded to bf16 first: what the unfused autocast path adds)
+ *     xb_out  bf16 [M,N]  = bf16(x_inout)   (the A operand of the next norm-folded GEMM)
+ *     ss_out  fp32 [M,N/128]: ss[m,j] = sum of x_inout[m, 128 j .. 128 j + 127]^2 after the update
+ * x_inout, xb_out, ss_out have contiguous rows.  Shape limits of ug_gemm_bf16.  Replaces F.linear + ug_add_rmsnorm. */
+int ug_gemm_residual_bf16(const void* a, const void* w, float* x_inout, void* xb_out, float* ss_out, int M, int N, int K,
+                          int64_t lda, int64_t ldw, void* stream);
 
 /* Fused q/k/v projection of Qwen2Attention.forward: qkv bf16 [M,(Hq+2Hkv)*128] = a [w_q|w_k|w_v]^T + bias, then
  * apply_rotary_pos_emb (rotate_half convention) on the q and k heads in the epilogue of the same launch, and -- with a
@@ -190,7 +202,8 @@ int ug_gemm_bf16(const void* a, const void* w, const void* bias, void* out, int 
  * Row m is position m % L; cos/sin fp32 [L, 64].  head_dim must be 128. */
 int ug_qkv_rope_bf16(const void* a, const void* w_qkv, const void* bias_qkv, void* qkv_out, int M, int K,
                      int64_t lda, int64_t ldw, int64_t ldo, const float* cos, const float* sin, int L, int Hq, int Hkv,
-                     void* kv_cache_bf16 /* nullable */, int cache_L, int cache_row_offset, void* stream);
+                     void* kv_cache_bf16 /* nullable */, int cache_L, int cache_row_offset,
+                     const float* row_ss /* nullable: RMSNorm folding, see ug_gemm_bf16 */, int ss_parts, float rms_eps, void* stream);
 
 /* ---- MAGViT-v2 pixel decoder, memory-bound kernels -----------------------------
  * MAGVITv2.decode_code (models/multimodal_encoder/magvitv2.py:438-442) = LFQuantizer.get_codebook_entry (:217-230) +
@@ -218,11 +231,6 @@ int ug_bias_add_stats_nhwc_bf16(const void* a_bf16, const void* bias_a_bf16, con
 int ug_bias_add_nhwc_bf16(const void* a_bf16, const void* bias_a_bf16, const void* r_bf16, const void* bias_r_bf16, void* out_bf16,
                           int64_t rows, int C, void* stream);
 int ug_upsample2x_nhwc_bf16(const void* x_bf16, void* y_bf16, int B, int H, int W, int C, void* stream);
-
-/* test hook: float[2*128*128 + 2048] receiving the raw scores S and the bf16 probabilities P of the first kv tile
- * of the first query tile of (b=0, h=0), followed by 2048 cycle stamps of CTA (0,0,0) (tools/attn_timeline.py), of
- * subsequent ug_omni_attention_bf16 calls of this thread; NULL = off */
-void ug_debug_set_attn_dump(float* dump);
 
 #ifdef __cplusplus
 }

@@ -11,14 +11,23 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("UNIGEN_B200_LIB") or os.path.join(_HERE, "csrc", "libunigen_b200.so")   # env override: kernel experiments only
 
-UG_ABI_VERSION = 1
+UG_ABI_VERSION = 2
 SYMBOLS = (
     "ug_abi_version", "ug_last_error", "ug_decode_step_workspace_bytes", "ug_decode_step_bf16",
-    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_omni_attention_rows_bf16", "ug_debug_set_rowsum_out", "ug_debug_set_force_full_race", "ug_debug_set_decode_mode", "ug_debug_set_decode_stats", "ug_debug_set_attn_dump", "ug_add_rmsnorm", "ug_rope_qk", "ug_swiglu", "ug_embed_rows", "ug_gemm_bf16", "ug_qkv_rope_bf16", "ug_lfq_unpack_bf16", "ug_groupnorm_workspace_floats", "ug_groupnorm_nhwc_bf16", "ug_bias_add_nhwc_bf16", "ug_bias_add_stats_nhwc_bf16", "ug_cfg_mix_bf16",
+    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_omni_attention_rows_bf16", "ug_add_rmsnorm", "ug_rope_qk", "ug_swiglu", "ug_embed_rows", "ug_gemm_bf16", "ug_gemm_residual_bf16", "ug_qkv_rope_bf16", "ug_lfq_unpack_bf16", "ug_groupnorm_workspace_floats", "ug_groupnorm_nhwc_bf16", "ug_bias_add_nhwc_bf16", "ug_bias_add_stats_nhwc_bf16", "ug_cfg_mix_bf16",
     "ug_upsample2x_nhwc_bf16",
 )
 
+# include/unigen_b200_test.h: the same entry points with explicit, per-call test instrumentation (stateless)
+TEST_SYMBOLS = ("ugt_decode_step_bf16", "ugt_omni_attention_rows_bf16")
+
 _lib = None
+
+
+class DecodeTestOptions(ctypes.Structure):
+    """ugt_decode_options of include/unigen_b200_test.h."""
+    _fields_ = [("rowsum_out", ctypes.c_void_p), ("force_exact_bits", ctypes.c_int), ("exact_kernel", ctypes.c_int),
+                ("stats", ctypes.c_void_p)]
 
 
 class UnigenB200Error(RuntimeError):
@@ -34,7 +43,7 @@ def lib() -> ctypes.CDLL:
             f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc -gencode arch=compute_100a,code=sm_100a).  There is no fallback path.")
     L = ctypes.CDLL(LIB_PATH)
-    for s in SYMBOLS:
+    for s in SYMBOLS + TEST_SYMBOLS:
         if not hasattr(L, s):
             raise UnigenB200Error(f"{LIB_PATH} does not export {s}")
     c = ctypes
@@ -69,16 +78,10 @@ def lib() -> ctypes.CDLL:
         c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_float,
         c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_int64,
         c.c_void_p]
-    L.ug_debug_set_rowsum_out.restype = None
-    L.ug_debug_set_rowsum_out.argtypes = [c.c_void_p]
-    L.ug_debug_set_force_full_race.restype = None
-    L.ug_debug_set_force_full_race.argtypes = [c.c_int]
-    L.ug_debug_set_decode_mode.restype = None
-    L.ug_debug_set_decode_mode.argtypes = [c.c_int]
-    L.ug_debug_set_decode_stats.restype = None
-    L.ug_debug_set_decode_stats.argtypes = [c.c_void_p]
-    L.ug_debug_set_attn_dump.restype = None
-    L.ug_debug_set_attn_dump.argtypes = [c.c_void_p]
+    L.ugt_decode_step_bf16.restype = c.c_int
+    L.ugt_decode_step_bf16.argtypes = L.ug_decode_step_bf16.argtypes + [c.POINTER(DecodeTestOptions)]
+    L.ugt_omni_attention_rows_bf16.restype = c.c_int
+    L.ugt_omni_attention_rows_bf16.argtypes = L.ug_omni_attention_rows_bf16.argtypes + [c.c_void_p]
     L.ug_add_rmsnorm.restype = c.c_int
     L.ug_add_rmsnorm.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_float, c.c_void_p]
     L.ug_rope_qk.restype = c.c_int
@@ -87,14 +90,17 @@ def lib() -> ctypes.CDLL:
     L.ug_swiglu.restype = c.c_int
     L.ug_swiglu.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_void_p]
     L.ug_embed_rows.restype = c.c_int
-    L.ug_embed_rows.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_int64, c.c_void_p]
+    L.ug_embed_rows.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_int64, c.c_void_p]
     L.ug_gemm_bf16.restype = c.c_int
     L.ug_gemm_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int,
-                               c.c_int64, c.c_int64, c.c_int64, c.c_int, c.c_void_p]
+                               c.c_int64, c.c_int64, c.c_int64, c.c_int, c.c_void_p, c.c_int, c.c_float, c.c_void_p]
+    L.ug_gemm_residual_bf16.restype = c.c_int
+    L.ug_gemm_residual_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int,
+                                        c.c_int64, c.c_int64, c.c_void_p]
     L.ug_qkv_rope_bf16.restype = c.c_int
     L.ug_qkv_rope_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int,
                                    c.c_int64, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int,
-                                   c.c_void_p, c.c_int, c.c_int, c.c_void_p]
+                                   c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_float, c.c_void_p]
     L.ug_lfq_unpack_bf16.restype = c.c_int
     L.ug_lfq_unpack_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_void_p]
     L.ug_groupnorm_workspace_floats.restype = c.c_size_t

@@ -193,10 +193,43 @@ __global__ void __launch_bounds__(256) embed_rows_kernel(float4* __restrict__ x,
     }
 }
 
-cudaError_t launch_embed_rows(float* x, const void* table, const int64_t* tokens, int64_t M, int H, int64_t vocab,
+// the same gather, one warp per row, that also leaves what the norm-folded GEMMs consume (gemm_tc.cu): xb = bf16(x) (here simply the
+// table row) and the per-128-column partial sums of x^2 (fp32 [M, H/128]); H % 256 == 0
+__global__ void __launch_bounds__(256) embed_rows_norm_kernel(float4* __restrict__ x, uint4* __restrict__ xb, float* __restrict__ ss,
+                                                              const uint4* __restrict__ table, const int64_t* __restrict__ tokens,
+                                                              int64_t M, int Hv, int64_t vocab)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= M) return;
+    int64_t tok = tokens[m];
+    tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+    for (int i = 0; i < Hv / 32; ++i) {
+        const int c = i * 32 + lane;                       // 8-element vector index inside the row; 16 vectors = one 128-column block
+        const uint4 e = table[tok * Hv + c];
+        const float v[8] = {bf_lo(e.x), bf_hi(e.x), bf_lo(e.y), bf_hi(e.y), bf_lo(e.z), bf_hi(e.z), bf_lo(e.w), bf_hi(e.w)};
+        x[2 * (m * Hv + c)] = make_float4(v[0], v[1], v[2], v[3]);
+        x[2 * (m * Hv + c) + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        xb[m * Hv + c] = e;
+        float sq = v[0] * v[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) sq = fmaf(v[k], v[k], sq);
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        if ((lane & 15) == 0) ss[m * (Hv / 16) + 2 * i + (lane >> 4)] = sq;
+    }
+}
+
+cudaError_t launch_embed_rows(float* x, void* xb, float* ss, const void* table, const int64_t* tokens, int64_t M, int H, int64_t vocab,
                               cudaStream_t stream)
 {
     if (H % 8 != 0 || M <= 0) return cudaErrorInvalidValue;
+    if (xb || ss) {
+        if (!xb || !ss || H % 256 != 0) return cudaErrorInvalidValue;
+        embed_rows_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, stream>>>((float4*)x, (uint4*)xb, ss, (const uint4*)table, tokens, M,
+                                                                            H / 8, vocab);
+        return cudaGetLastError();
+    }
     const int64_t total = M * (H / 8);
     unsigned grid = (unsigned)((total + 255) / 256);
     if (grid > 148u * 32u) grid = 148u * 32u;

@@ -20,8 +20,10 @@ cudaError_t launch_rope_qk(void* qkv_bf16, const float* cos, const float* sin, i
 // act[M,I] = bf16( silu(g) * u ) with gu bf16 [M, 2*I] = [g | u].  I % 8 == 0.
 cudaError_t launch_swiglu(const void* gu_bf16, void* act_bf16, int64_t M, int I, cudaStream_t stream);
 
-// x[m,:] = float(table[token[m], :]) ; table bf16 [vocab,H], tokens int64 [M]
-cudaError_t launch_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64_t M, int H, int64_t vocab,
-                              cudaStream_t stream);
+// x[m,:] = float(table[token[m], :]) ; table bf16 [vocab,H], tokens int64 [M].  With xb / ss (both or neither; H % 256 == 0):
+// xb[m,:] = bf16(x[m,:]) and ss[m, j] = sum of x[m, 128 j .. 128 j + 127]^2 (fp32 [M, H/128]) -- the operands of the
+// norm-folded GEMMs (gemm_tc.h).
+cudaError_t launch_embed_rows(float* x, void* xb_bf16, float* ss, const void* table_bf16, const int64_t* tokens, int64_t M, int H,
+                              int64_t vocab, cudaStream_t stream);
 
 }  // namespace ugk

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SOURCES = ["ug_capi.cu", "decode_step.cu", "decode_fast.cu", "omni_attention.cu", "backbone_ops.cu", "gemm_tc.cu", "magvit_ops.cu"]
 HEADERS = ["ug_math.cuh", "ug_ptx.cuh", "decode_step.h", "omni_attention.h", "backbone_ops.h", "gemm_tc.h", "magvit_ops.h",
-           os.path.join(ROOT, "include", "unigen_b200.h")]
+           os.path.join(ROOT, "include", "unigen_b200.h"), os.path.join(ROOT, "include", "unigen_b200_test.h")]
 OUT = os.path.join(HERE, "libunigen_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-lcuda"]

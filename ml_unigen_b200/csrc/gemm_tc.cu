@@ -6,6 +6,12 @@
 //                  [M, 2I] gate|up activation (588 MB per layer at config 2) is never written to HBM
 //   mode q/k/v   : qkv = rope(x [Wq|Wk|Wv]^T + bias)              q_proj/k_proj/v_proj + apply_rotary_pos_emb, and the rotated
 //                  k rows / the v rows written to the K/V cache of the text-prefix reuse in the same epilogue
+//   mode residual: x += bf16(a W^T); xb = bf16(x); ss = sum x^2   o_proj / down_proj + the residual add of Qwen2DecoderLayer + the
+//                  statistics of the Qwen2RMSNorm that follows: the separate add+RMSNorm pass over HBM no longer exists
+// RMSNorm folding (all consumer modes, `row_ss` != null): Qwen2RMSNorm commutes with the linear layer that follows it,
+//   (g * x / rms) W^T = (1 / rms) * (x (W diag g)^T), so the A operand is bf16(x) as the residual-mode epilogue left it, g is
+//   folded into the weight columns once at load time, and 1 / rms = rsqrt(sum_p ss[m, p] / K + eps) scales row m of the
+//   accumulator in the epilogue (the partial sums are added in a fixed order: deterministic).
 //
 // Shape of the kernel (sm_100a only):
 //   * cluster of 2 CTAs = one SM pair; the pair owns a 256 x 256 output tile; `tcgen05.mma.cta_group::2.kind::f16`
@@ -64,6 +70,14 @@ struct GemmParams {
     const float* rope_sin;
     __nv_bfloat16* kv_cache;                  // nullable: bf16 [B, cache_L, 2, Hkv, 128]
     int rope_L, rope_Hq, rope_Hkv, cache_L, cache_row0;
+    // RMSNorm folding: fp32 [M, ss_parts] partial sums of squares of the rows of A's fp32 source (nullable)
+    const float* row_ss;
+    int ss_parts;
+    float rms_eps;
+    // residual mode: x fp32 [M, N] (+= bf16(acc)), xb bf16 [M, N] = bf16(x), ss_out fp32 [M, N / 128]
+    float* res_x;
+    __nv_bfloat16* res_xb;
+    float* res_ss;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -210,6 +224,24 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // the arithmetic of ug_swiglu (backbone_ops.cu) on the bf16-rounded GEMM outputs, so that the fused and the unfused
 // path differ only by the accumulation order inside the GEMM
 __device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(g, 1.0f + __expf(-g)) * u; }
+
+// 1 / rms of row m (RMSNorm folding); the partial sums are added in index order
+__device__ __forceinline__ float row_rstd(const GemmParams& p, int m)
+{
+    if (!p.row_ss) return 1.0f;
+    float s = 0.0f;
+    if (m < p.M) {
+        const float* sp = p.row_ss + (int64_t)m * p.ss_parts;
+        for (int j = 0; j < p.ss_parts; ++j) s += __ldg(sp + j);
+    }
+    return rsqrtf(s / (float)p.K + p.rms_eps);
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
@@ -360,6 +392,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     for (int j = 0; j < 32; ++j) { rope_c[j] = 1.0f; rope_s[j] = 0.0f; }
                 }
             }
+            const float rstd = row_rstd(p, m0 + r);
+            if (MODE == kGemmResidual) {
+                // the x tile this CTA is about to read-modify-write: into L2 while the MMAs of the unit still run
+                const int et = (int)threadIdx.x - 128, prow = m0 + (et & 127), ph = et >> 7;
+                if (prow < p.M && (half < 0 || ph == half))
+                    prefetch_l2_bulk(p.res_x + (int64_t)prow * p.N + nb * kGN + ph * 128, 512u);
+            }
             bar_wait(&bars->acc_full[as], aph);
             tc_fence_after();
             const uint32_t acc = lane_addr + as * 256u;
@@ -384,8 +423,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     uint32_t o[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
-                        const float g0 = bf16_round(__uint_as_float(g[2 * q])), g1 = bf16_round(__uint_as_float(g[2 * q + 1]));
-                        const float u0 = bf16_round(__uint_as_float(u[2 * q])), u1 = bf16_round(__uint_as_float(u[2 * q + 1]));
+                        const float g0 = bf16_round(__uint_as_float(g[2 * q]) * rstd), g1 = bf16_round(__uint_as_float(g[2 * q + 1]) * rstd);
+                        const float u0 = bf16_round(__uint_as_float(u[2 * q]) * rstd), u1 = bf16_round(__uint_as_float(u[2 * q + 1]) * rstd);
                         o[q] = pack_bf16(silu_mul(g0, u0), silu_mul(g1, u1));
                     }
                     uint8_t* panel = stg + (cc >> 1) * 16384 + stg_row;
@@ -444,10 +483,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             float x1[8], x2[8];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                x1[2 * e] = bf16_round(__uint_as_float(lo[8 * j + 2 * e]) + __uint_as_float(bw1[e] << 16));
-                                x1[2 * e + 1] = bf16_round(__uint_as_float(lo[8 * j + 2 * e + 1]) + __uint_as_float(bw1[e] & 0xffff0000u));
-                                x2[2 * e] = bf16_round(__uint_as_float(hi[8 * j + 2 * e]) + __uint_as_float(bw2[e] << 16));
-                                x2[2 * e + 1] = bf16_round(__uint_as_float(hi[8 * j + 2 * e + 1]) + __uint_as_float(bw2[e] & 0xffff0000u));
+                                x1[2 * e] = bf16_round(fmaf(__uint_as_float(lo[8 * j + 2 * e]), rstd, __uint_as_float(bw1[e] << 16)));
+                                x1[2 * e + 1] = bf16_round(fmaf(__uint_as_float(lo[8 * j + 2 * e + 1]), rstd, __uint_as_float(bw1[e] & 0xffff0000u)));
+                                x2[2 * e] = bf16_round(fmaf(__uint_as_float(hi[8 * j + 2 * e]), rstd, __uint_as_float(bw2[e] << 16)));
+                                x2[2 * e + 1] = bf16_round(fmaf(__uint_as_float(hi[8 * j + 2 * e + 1]), rstd, __uint_as_float(bw2[e] & 0xffff0000u)));
                             }
                             if (rot) {
 #pragma unroll
@@ -491,7 +530,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 for (int hh = h0; hh < h1; ++hh) {
                     const uint32_t acc_h = acc + (half < 0 ? (uint32_t)hh * 128u : 0u);
                     const int col0 = nb * kGN + hh * 128;             // first output column of this 128-column half
-                    if (issuer) bulk_wait_read0();
+                    if (MODE != kGemmResidual && issuer) bulk_wait_read0();
                     epi_bar();
 #pragma unroll 1
                     for (int cc = 2 * cg; cc < 2 * cg + 2; ++cc) {
@@ -510,12 +549,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     const float b0 = __uint_as_float(bw[e] << 16), b1 = __uint_as_float(bw[e] & 0xffff0000u);
-                                    o[4 * j + e] = pack_bf16(__uint_as_float(v[8 * j + 2 * e]) + b0, __uint_as_float(v[8 * j + 2 * e + 1]) + b1);
+                                    o[4 * j + e] = pack_bf16(fmaf(__uint_as_float(v[8 * j + 2 * e]), rstd, b0), fmaf(__uint_as_float(v[8 * j + 2 * e + 1]), rstd, b1));
                                 }
                             }
                         } else {
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) o[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+                            for (int q = 0; q < 16; ++q) o[q] = pack_bf16(__uint_as_float(v[2 * q]) * rstd, __uint_as_float(v[2 * q + 1]) * rstd);
                         }
                         {
                             uint8_t* panel = stg + (cc >> 1) * 16384 + stg_row;
@@ -526,12 +565,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             }
                         }
                     }
-                    fence_async_smem();
-                    epi_bar();
-                    if (issuer && m0 < p.M) {
-                        tma_store_2d(&tm_o, s_u32(stg), col0, m0);
-                        tma_store_2d(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
-                        bulk_commit();
+                    if (MODE == kGemmResidual) {
+                        // second pass, row-major and coalesced: the staging tile now holds bf16(acc) = the value the unfused
+                        // linear layer would have written.  Warp w takes rows 16 w .. 16 w + 15; a lane owns 4 consecutive
+                        // columns, so one warp access is one 512-byte row segment of x (fp32) / 256 bytes of xb (bf16).
+                        epi_bar();
+                        const int w8 = warp - 4;
+                        const uint32_t lane_off = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(lane & 1) * 8u;
+                        const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
+#pragma unroll
+                        for (int bch = 0; bch < 2; ++bch) {
+                            float4 xv[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int row = w8 * 16 + bch * 8 + i;
+                                xv[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                if (m0 + row < p.M)
+                                    xv[i] = *reinterpret_cast<const float4*>(p.res_x + (int64_t)(m0 + row) * p.N + col0 + lane * 4);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int row = w8 * 16 + bch * 8 + i;
+                                const uint2 d = *reinterpret_cast<const uint2*>(stg + lane_off + (uint32_t)row * 128u +
+                                                                                ((lane_chunk ^ (uint32_t)(row & 7)) << 4));
+                                float4 y;
+                                y.x = xv[i].x + bf16lo(d.x);
+                                y.y = xv[i].y + bf16hi(d.x);
+                                y.z = xv[i].z + bf16lo(d.y);
+                                y.w = xv[i].w + bf16hi(d.y);
+                                float sq = y.x * y.x;
+                                sq = fmaf(y.y, y.y, sq);
+                                sq = fmaf(y.z, y.z, sq);
+                                sq = fmaf(y.w, y.w, sq);
+#pragma unroll
+                                for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+                                if (m0 + row < p.M) {
+                                    const int64_t gi = (int64_t)(m0 + row) * p.N + col0 + lane * 4;
+                                    *reinterpret_cast<float4*>(p.res_x + gi) = y;
+                                    *reinterpret_cast<uint2*>(p.res_xb + gi) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+                                    if (lane == 0) p.res_ss[(int64_t)(m0 + row) * (p.N >> 7) + (col0 >> 7)] = sq;
+                                }
+                            }
+                        }
+                    } else {
+                        fence_async_smem();
+                        epi_bar();
+                        if (issuer && m0 < p.M) {
+                            tma_store_2d(&tm_o, s_u32(stg), col0, m0);
+                            tma_store_2d(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
+                            bulk_commit();
+                        }
                     }
                 }
             }
@@ -581,19 +664,22 @@ bool make_map_2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t ro
 
 int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* msg, size_t msg_len)
 {
-    if (g.mode != kGemmPlain && g.mode != kGemmSwiGLU && g.mode != kGemmQkvRope) { snprintf(msg, msg_len, "gemm: unsupported mode %d", g.mode); return -4; }
+    if (g.mode != kGemmPlain && g.mode != kGemmSwiGLU && g.mode != kGemmQkvRope && g.mode != kGemmResidual) { snprintf(msg, msg_len, "gemm: unsupported mode %d", g.mode); return -4; }
     if (g.M < 1 || g.N < kGN || g.N % kGN || g.K < kGK || g.K % kGK) {
         snprintf(msg, msg_len, "gemm: need N %% 256 == 0 and K %% 64 == 0 (M=%d N=%d K=%d)", g.M, g.N, g.K);
         return -4;
     }
-    if (g.lda % 8 || g.ldw % 8 || g.ldo % 8) { snprintf(msg, msg_len, "gemm: row strides must be multiples of 8 elements"); return -5; }
+    if (g.lda % 8 || g.ldw % 8 || (g.mode != kGemmResidual && g.ldo % 8)) { snprintf(msg, msg_len, "gemm: row strides must be multiples of 8 elements"); return -5; }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { snprintf(msg, msg_len, "cuTensorMapEncodeTiled entry point not available"); return -6; }
     const int n_out = g.mode == kGemmSwiGLU ? g.N / 2 : g.N;
     CUtensorMap ta, tw, twh, to;
+    const bool residual = g.mode == kGemmResidual;       // writes x / xb / ss with plain stores: no output tensor map
+    if (residual && (!g.res_x || !g.res_xb || !g.res_ss)) { snprintf(msg, msg_len, "gemm: the residual mode needs x, xb and ss"); return -1; }
+    if (g.row_ss && g.ss_parts < 1) { snprintf(msg, msg_len, "gemm: row_ss needs ss_parts >= 1"); return -4; }
     if (!make_map_2d(enc, &ta, g.a, g.M, g.K, g.lda) || !make_map_2d(enc, &tw, g.w, g.N, g.K, g.ldw) ||
         !make_map_2d(enc, &twh, g.w, g.N, g.K, g.ldw, 64) ||
-        !make_map_2d(enc, &to, g.out, g.M, n_out, g.ldo)) {
+        !(residual ? make_map_2d(enc, &to, g.a, g.M, g.K, g.lda) : make_map_2d(enc, &to, g.out, g.M, n_out, g.ldo))) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled rejected the a/w/out layout");
         return -3;
     }
@@ -607,6 +693,8 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     p.rope_cos = g.rope_cos; p.rope_sin = g.rope_sin;
     p.kv_cache = reinterpret_cast<__nv_bfloat16*>(g.kv_cache);
     p.rope_L = g.rope_L; p.rope_Hq = g.rope_Hq; p.rope_Hkv = g.rope_Hkv; p.cache_L = g.cache_L; p.cache_row0 = g.cache_row0;
+    p.row_ss = g.row_ss; p.ss_parts = g.ss_parts; p.rms_eps = g.rms_eps;
+    p.res_x = g.res_x; p.res_xb = reinterpret_cast<__nv_bfloat16*>(g.res_xb); p.res_ss = g.res_ss;
     if (g.mode == kGemmQkvRope && (!g.rope_cos || !g.rope_sin || g.rope_L < 1 || g.N != (g.rope_Hq + 2 * g.rope_Hkv) * 128)) {
         snprintf(msg, msg_len, "gemm: q/k/v + RoPE mode needs cos/sin tables, rope_L >= 1 and N == (Hq + 2 Hkv) * 128");
         return -4;
@@ -618,6 +706,7 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmSwiGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmQkvRope>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<kGemmResidual>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
@@ -633,6 +722,7 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     switch (g.mode) {
         case kGemmPlain: gemm_tc_kernel<kGemmPlain><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
         case kGemmSwiGLU: gemm_tc_kernel<kGemmSwiGLU><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
+        case kGemmResidual: gemm_tc_kernel<kGemmResidual><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
         default: gemm_tc_kernel<kGemmQkvRope><<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, twh, to, p); break;
     }
     cudaError_t e = cudaGetLastError();

@@ -12,6 +12,7 @@ enum GemmMode : int {
     kGemmSwiGLU = 1,    // out bf16 [M,N/2] = silu(g) * u, W rows interleaved in blocks of 128: [g_0..127 | u_0..127 | g_128.. ]
     kGemmQkvRope = 2,   // out bf16 [M,N]   = rope(A W^T + bias) on the q and k heads (head_dim 128), v heads copied; k/v rows also
                         // written to the K/V cache
+    kGemmResidual = 3,  // x fp32 [M,N] += bf16(A W^T); xb bf16 [M,N] = bf16(x); ss fp32 [M,N/128] = per-128-column sums of x^2
 };
 
 struct GemmArgs {
@@ -27,6 +28,14 @@ struct GemmArgs {
     const float* rope_sin = nullptr;
     void* kv_cache = nullptr;          // nullable: bf16 [B, cache_L, 2, Hkv, 128]
     int rope_L = 0, rope_Hq = 0, rope_Hkv = 0, cache_L = 0, cache_row0 = 0;
+    // RMSNorm folding (plain / SwiGLU / q/k/v modes): row m of the accumulator is scaled by rsqrt(sum_p row_ss[m,p] / K + rms_eps)
+    const float* row_ss = nullptr;     // fp32 [M, ss_parts] or null
+    int ss_parts = 0;
+    float rms_eps = 0.0f;
+    // kGemmResidual only (contiguous rows of N elements)
+    float* res_x = nullptr;
+    void* res_xb = nullptr;
+    float* res_ss = nullptr;
 };
 
 int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* msg, size_t msg_len);

@@ -776,8 +776,6 @@ static bool make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int L,
     return r == CUDA_SUCCESS;
 }
 
-static thread_local float* g_attn_dbg = nullptr;
-void set_attn_debug(float* p) { g_attn_dbg = p; }
 
 int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, char* msg, size_t msg_len)
 {
@@ -809,7 +807,7 @@ int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, c
         if (ov && atoi(ov) >= 0 && atoi(ov) <= n_full) k = atoi(ov);
         p.n_split = k;
     }
-    p.dbg = g_attn_dbg;
+    p.dbg = a.dbg;
     static bool attr_set[64] = {};                       // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);

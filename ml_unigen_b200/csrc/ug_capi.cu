@@ -5,16 +5,12 @@
 #include <cstring>
 
 #include "unigen_b200.h"
+#include "unigen_b200_test.h"
 #include "decode_step.h"
 #include "omni_attention.h"
 #include "backbone_ops.h"
 #include "gemm_tc.h"
 #include "magvit_ops.h"
-
-float* ugk_debug_rowsum_out();
-int ugk_debug_force_full_race();
-int ugk_debug_decode_mode();
-unsigned* ugk_debug_decode_stats();
 
 namespace {
 
@@ -54,6 +50,23 @@ int sm_count(int* cc_major)
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ug_decode_step_bf16 and its test-only twin ugt_decode_step_bf16 (explicit, stateless options; NULL = production behaviour)
+int decode_step_impl(const void* logits, const void* uncond_logits, float guidance_scale,
+                     int64_t* ids_inout, int64_t* sampled_out, uint8_t* mask_out,
+                     float* sel_prob_out, float* conf_out,
+                     const float* q_noise, const float* u_noise,
+                     uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
+                     int B, int N, int V, int64_t mask_token_id, int mask_len_cap, float temperature,
+                     void* workspace, size_t workspace_bytes, void* stream, const ugt_decode_options* opts);
+
+int attention_impl(const void* q, const void* k, const void* v, void* out,
+                   const int32_t* pad_len, const int32_t* soi_idx,
+                   int B, int L, int Lq, int q_row_offset, int Hq, int Hkv, int D, float scale,
+                   int64_t q_stride_b, int64_t q_stride_l, int64_t q_stride_h,
+                   int64_t kv_stride_b, int64_t kv_stride_l, int64_t kv_stride_h,
+                   int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
+                   void* stream, float* debug_dump);
+
 }  // namespace
 
 extern "C" {
@@ -77,6 +90,35 @@ int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float gui
                         uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
                         int B, int N, int V, int64_t mask_token_id, int mask_len_cap, float temperature,
                         void* workspace, size_t workspace_bytes, void* stream)
+{
+    return decode_step_impl(logits, uncond_logits, guidance_scale, ids_inout, sampled_out, mask_out, sel_prob_out, conf_out, q_noise,
+                            u_noise, philox_seed, philox_offset, batch_offset, B, N, V, mask_token_id, mask_len_cap, temperature,
+                            workspace, workspace_bytes, stream, nullptr);
+}
+
+int ugt_decode_step_bf16(const void* logits, const void* uncond_logits, float guidance_scale,
+                         int64_t* ids_inout, int64_t* sampled_out, uint8_t* mask_out,
+                         float* sel_prob_out, float* conf_out,
+                         const float* q_noise, const float* u_noise,
+                         uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
+                         int B, int N, int V, int64_t mask_token_id, int mask_len_cap, float temperature,
+                         void* workspace, size_t workspace_bytes, void* stream, const ugt_decode_options* opts)
+{
+    return decode_step_impl(logits, uncond_logits, guidance_scale, ids_inout, sampled_out, mask_out, sel_prob_out, conf_out, q_noise,
+                            u_noise, philox_seed, philox_offset, batch_offset, B, N, V, mask_token_id, mask_len_cap, temperature,
+                            workspace, workspace_bytes, stream, opts);
+}
+
+}  // extern "C"
+
+namespace {
+int decode_step_impl(const void* logits, const void* uncond_logits, float guidance_scale,
+                     int64_t* ids_inout, int64_t* sampled_out, uint8_t* mask_out,
+                     float* sel_prob_out, float* conf_out,
+                     const float* q_noise, const float* u_noise,
+                     uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
+                     int B, int N, int V, int64_t mask_token_id, int mask_len_cap, float temperature,
+                     void* workspace, size_t workspace_bytes, void* stream, const ugt_decode_options* opts)
 {
     if (!logits || !ids_inout || !sampled_out || !mask_out || !workspace)
         return fail(UG_ERR_NULL, "ug_decode_step_bf16: logits, ids_inout, sampled_out, mask_out and workspace are required");
@@ -103,8 +145,8 @@ int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float gui
     a.mask = mask_out;
     a.sel_prob_out = sel_prob_out;
     a.conf_out = conf_out;
-    a.rowsum_out = ugk_debug_rowsum_out();
-    a.force_full_race = ugk_debug_force_full_race();
+    a.rowsum_out = opts ? opts->rowsum_out : nullptr;
+    a.force_full_race = opts ? opts->force_exact_bits : 0;
     a.q_noise = q_noise;
     a.u_noise = u_noise;
     a.seed = philox_seed;
@@ -118,16 +160,19 @@ int ug_decode_step_bf16(const void* logits, const void* uncond_logits, float gui
     a.ticket = w;
     a.cta_done = w + 1;
     a.slots = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + 256);
-    a.stats = ugk_debug_decode_stats();
+    a.stats = opts ? opts->stats : nullptr;
     // The certified fast path (decode_fast.cu: row kernel + selection kernel, two launches on `stream`) serves the production configuration (in-kernel noise, no CFG,
     // V <= 8192); injected race noise, CFG and V = 16384 run on the exact-arithmetic kernel (decode_step.cu).
     // Both produce the ids and masks of the same specification.
-    const bool fast = ugk_debug_decode_mode() == 0 && ugk::decode_fast_supported(a);
+    const bool fast = !(opts && opts->exact_kernel) && ugk::decode_fast_supported(a);
     cudaError_t e = fast ? ugk::launch_decode_fast(a, sms, static_cast<cudaStream_t>(stream))
                          : ugk::launch_decode_step(a, sms, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "ug_decode_step_bf16 launch");
     return UG_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int ug_mask_by_random_topk(const float* probs, const int64_t* mask_len, const float* u_noise,
                            uint64_t philox_seed, uint64_t philox_offset, int64_t batch_offset,
@@ -171,6 +216,33 @@ int ug_omni_attention_rows_bf16(const void* q, const void* k, const void* v, voi
                                 int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
                                 void* stream)
 {
+    return attention_impl(q, k, v, out, pad_len, soi_idx, B, L, Lq, q_row_offset, Hq, Hkv, D, scale, q_stride_b, q_stride_l, q_stride_h,
+                          kv_stride_b, kv_stride_l, kv_stride_h, o_stride_b, o_stride_l, o_stride_h, stream, nullptr);
+}
+
+int ugt_omni_attention_rows_bf16(const void* q, const void* k, const void* v, void* out,
+                                 const int32_t* pad_len, const int32_t* soi_idx,
+                                 int B, int L, int Lq, int q_row_offset, int Hq, int Hkv, int D, float scale,
+                                 int64_t q_stride_b, int64_t q_stride_l, int64_t q_stride_h,
+                                 int64_t kv_stride_b, int64_t kv_stride_l, int64_t kv_stride_h,
+                                 int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
+                                 void* stream, float* debug_dump)
+{
+    return attention_impl(q, k, v, out, pad_len, soi_idx, B, L, Lq, q_row_offset, Hq, Hkv, D, scale, q_stride_b, q_stride_l, q_stride_h,
+                          kv_stride_b, kv_stride_l, kv_stride_h, o_stride_b, o_stride_l, o_stride_h, stream, debug_dump);
+}
+
+}  // extern "C"
+
+namespace {
+int attention_impl(const void* q, const void* k, const void* v, void* out,
+                   const int32_t* pad_len, const int32_t* soi_idx,
+                   int B, int L, int Lq, int q_row_offset, int Hq, int Hkv, int D, float scale,
+                   int64_t q_stride_b, int64_t q_stride_l, int64_t q_stride_h,
+                   int64_t kv_stride_b, int64_t kv_stride_l, int64_t kv_stride_h,
+                   int64_t o_stride_b, int64_t o_stride_l, int64_t o_stride_h,
+                   void* stream, float* debug_dump)
+{
     if (!q || !k || !v || !out || !pad_len || !soi_idx) return fail(UG_ERR_NULL, "ug_omni_attention_bf16: null pointer");
     if (D != 128 || Hkv < 1 || Hq % Hkv != 0 || B < 1 || L < 1 || L > 4096 || Lq < 1 || q_row_offset < 0 || q_row_offset + Lq > L)
         return fail(UG_ERR_SHAPE, "ug_omni_attention_bf16: B=%d L=%d Lq=%d q0=%d Hq=%d Hkv=%d D=%d unsupported (D=128, Hq%%Hkv==0, "
@@ -189,11 +261,15 @@ int ug_omni_attention_rows_bf16(const void* q, const void* k, const void* v, voi
     a.q_sb = q_stride_b; a.q_sl = q_stride_l; a.q_sh = q_stride_h;
     a.kv_sb = kv_stride_b; a.kv_sl = kv_stride_l; a.kv_sh = kv_stride_h;
     a.o_sb = o_stride_b; a.o_sl = o_stride_l; a.o_sh = o_stride_h;
+    a.dbg = debug_dump;
     char msg[256] = "";
     int rc = ugk::launch_omni_attention(a, sms, static_cast<cudaStream_t>(stream), msg, sizeof msg);
     if (rc != 0) { snprintf(g_err, sizeof g_err, "ug_omni_attention_bf16: %s", msg); return rc; }
     return UG_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* out,
                            const int32_t* pad_len, const int32_t* soi_idx,
@@ -210,35 +286,14 @@ int ug_omni_attention_bf16(const void* q, const void* k, const void* v, void* ou
 
 }  // extern "C"
 
-// test hook: when set, the next decode steps issued from this thread also write the softmax
-// denominators (float [B,N], 0 for known rows) so tests can compare them bit for bit.
-static thread_local float* g_rowsum_out = nullptr;
-extern "C" void ug_debug_set_rowsum_out(float* p) { g_rowsum_out = p; }
-float* ugk_debug_rowsum_out() { return g_rowsum_out; }
-
-// test hook: force the exact whole-row evaluation of the race (the e^-16 fallback) on every row
-static thread_local int g_force_full_race = 0;
-extern "C" void ug_debug_set_force_full_race(int on) { g_force_full_race = on; }
-int ugk_debug_force_full_race() { return g_force_full_race; }
-
-// test hook: 0 = automatic kernel choice (certified fast kernel when eligible), 1 = always the exact-arithmetic kernel
-static thread_local int g_decode_mode = 0;
-extern "C" void ug_debug_set_decode_mode(int mode) { g_decode_mode = mode; }
-int ugk_debug_decode_mode() { return g_decode_mode; }
-
-// test hook: device uint32[4] counters of the fast kernel's exact paths (NULL = off)
-static thread_local unsigned* g_decode_stats = nullptr;
-extern "C" void ug_debug_set_decode_stats(unsigned* p) { g_decode_stats = p; }
-unsigned* ugk_debug_decode_stats() { return g_decode_stats; }
-
-extern "C" void ug_debug_set_attn_dump(float* p) { ugk::set_attn_debug(p); }
-
 // ---- row-wise backbone kernels ---------------------------------------------------------------------
 extern "C" int ug_add_rmsnorm(float* x, const void* delta_bf16, const void* weight_bf16, void* out_bf16,
                               int64_t M, int H, float eps, void* stream)
 {
     if (!x || !weight_bf16 || !out_bf16) return fail(UG_ERR_NULL, "ug_add_rmsnorm: x, weight, out are required");
-    if (M < 1 || H % 256 != 0 || H > 8192) return fail(UG_ERR_SHAPE, "ug_add_rmsnorm: M=%lld H=%d unsupported (H %% 256 == 0, H <= 8192)", (long long)M, H);
+    const int vpl = H / 256;               // the instantiated row widths of add_rmsnorm_kernel
+    if (M < 1 || H % 256 != 0 || !((vpl >= 1 && vpl <= 8) || (vpl <= 32 && vpl % 4 == 0)))
+        return fail(UG_ERR_SHAPE, "ug_add_rmsnorm: M=%lld H=%d unsupported (H = 256 k with k in 1..8, 12, 16, 20, 24, 28, 32)", (long long)M, H);
     if (!aligned16(x) || !aligned16(delta_bf16) || !aligned16(weight_bf16) || !aligned16(out_bf16))
         return fail(UG_ERR_ALIGN, "ug_add_rmsnorm: pointers must be 16-byte aligned");
     cudaError_t e = ugk::launch_add_rmsnorm(x, delta_bf16, weight_bf16, out_bf16, M, H, eps, static_cast<cudaStream_t>(stream));
@@ -252,7 +307,7 @@ extern "C" int ug_rope_qk(void* qkv_bf16, const float* cos, const float* sin, in
     if (!qkv_bf16 || !cos || !sin) return fail(UG_ERR_NULL, "ug_rope_qk: null pointer");
     if (M < 1 || L < 1 || D % 16 != 0 || Hq < 1 || Hkv < 1 || M % L != 0) return fail(UG_ERR_SHAPE, "ug_rope_qk: bad shape");
     if (kv_cache_bf16 && M % L != 0)
-        return fail(UG_ERR_SHAPE, "ug_qkv_rope_bf16: with a K/V cache M (%d) must be a whole number of sequences of L (%d) rows", M, L);
+        return fail(UG_ERR_SHAPE, "ug_rope_qk: with a K/V cache M (%lld) must be a whole number of sequences of L (%d) rows", (long long)M, L);
     if (kv_cache_bf16 && (cache_row_offset < 0 || cache_row_offset + L > cache_L))
         return fail(UG_ERR_SHAPE, "ug_rope_qk: cache window [%d, %d) outside cache_L=%d", cache_row_offset, cache_row_offset + L, cache_L);
     if (!aligned16(qkv_bf16) || !aligned16(cos) || !aligned16(sin) || !aligned16(kv_cache_bf16))
@@ -273,18 +328,21 @@ extern "C" int ug_swiglu(const void* gate_up_bf16, void* act_bf16, int64_t M, in
     return UG_OK;
 }
 
-extern "C" int ug_embed_rows(float* x, const void* table_bf16, const int64_t* tokens, int64_t M, int H, int64_t vocab, void* stream)
+extern "C" int ug_embed_rows(float* x, void* xb_bf16, float* ss, const void* table_bf16, const int64_t* tokens, int64_t M, int H,
+                             int64_t vocab, void* stream)
 {
     if (!x || !table_bf16 || !tokens) return fail(UG_ERR_NULL, "ug_embed_rows: null pointer");
-    if (M < 1 || H % 8 != 0 || vocab < 1) return fail(UG_ERR_SHAPE, "ug_embed_rows: bad shape");
-    if (!aligned16(x) || !aligned16(table_bf16)) return fail(UG_ERR_ALIGN, "ug_embed_rows: pointers must be 16-byte aligned");
-    cudaError_t e = ugk::launch_embed_rows(x, table_bf16, tokens, M, H, vocab, static_cast<cudaStream_t>(stream));
+    if ((xb_bf16 == nullptr) != (ss == nullptr)) return fail(UG_ERR_NULL, "ug_embed_rows: xb and ss come together (both or neither)");
+    if (M < 1 || H % 8 != 0 || vocab < 1 || (ss && H % 256 != 0))
+        return fail(UG_ERR_SHAPE, "ug_embed_rows: bad shape (H %% 8 == 0; H %% 256 == 0 with xb / ss)");
+    if (!aligned16(x) || !aligned16(table_bf16) || !aligned16(xb_bf16)) return fail(UG_ERR_ALIGN, "ug_embed_rows: pointers must be 16-byte aligned");
+    cudaError_t e = ugk::launch_embed_rows(x, xb_bf16, ss, table_bf16, tokens, M, H, vocab, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "ug_embed_rows launch");
     return UG_OK;
 }
 
 extern "C" int ug_gemm_bf16(const void* a, const void* w, const void* bias, void* out, int M, int N, int K,
-                            int64_t lda, int64_t ldw, int64_t ldo, int mode, void* stream)
+                            int64_t lda, int64_t ldw, int64_t ldo, int mode, const float* row_ss, int ss_parts, float rms_eps, void* stream)
 {
     if (!a || !w || !out) return fail(UG_ERR_NULL, "ug_gemm_bf16: null pointer");
     if (mode != UG_GEMM_PLAIN && mode != UG_GEMM_SWIGLU) return fail(UG_ERR_SHAPE, "ug_gemm_bf16: unknown mode %d", mode);
@@ -303,17 +361,45 @@ extern "C" int ug_gemm_bf16(const void* a, const void* w, const void* bias, void
     g.a = a; g.w = w; g.bias = bias; g.out = out;
     g.lda = lda; g.ldw = ldw; g.ldo = ldo;
     g.M = M; g.N = N; g.K = K; g.mode = mode;
+    if (row_ss && ss_parts < 1) return fail(UG_ERR_ARG, "ug_gemm_bf16: row_ss needs ss_parts >= 1");
+    g.row_ss = row_ss; g.ss_parts = ss_parts; g.rms_eps = rms_eps;
     char msg[256] = "";
     const int rc = ugk::launch_gemm_tc(g, sms, static_cast<cudaStream_t>(stream), msg, sizeof msg);
     if (rc != 0) return fail(rc, "ug_gemm_bf16: %s", msg);
     return UG_OK;
 }
 
+extern "C" int ug_gemm_residual_bf16(const void* a, const void* w, float* x_inout, void* xb_out, float* ss_out, int M, int N, int K,
+                                     int64_t lda, int64_t ldw, void* stream)
+{
+    if (!a || !w || !x_inout || !xb_out || !ss_out) return fail(UG_ERR_NULL, "ug_gemm_residual_bf16: null pointer");
+    if (M < 1 || N < 256 || N % 256 || K < 64 || K % 64)
+        return fail(UG_ERR_SHAPE, "ug_gemm_residual_bf16: need M >= 1, N %% 256 == 0, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+    if (lda < K || ldw < K || lda % 8 || ldw % 8)
+        return fail(UG_ERR_SHAPE, "ug_gemm_residual_bf16: row strides must cover the row and be multiples of 8 elements");
+    if (!aligned16(a) || !aligned16(w) || !aligned16(x_inout) || !aligned16(xb_out))
+        return fail(UG_ERR_ALIGN, "ug_gemm_residual_bf16: pointers must be 16-byte aligned");
+    int major = 0;
+    const int sms = sm_count(&major);
+    if (major != 10) return fail(UG_ERR_DEVICE, "ug_gemm_residual_bf16 needs an sm_100 device (tcgen05), found compute capability %d.x", major);
+    ugk::GemmArgs g;
+    g.a = a; g.w = w; g.bias = nullptr; g.out = nullptr;
+    g.lda = lda; g.ldw = ldw; g.ldo = N;
+    g.M = M; g.N = N; g.K = K; g.mode = ugk::kGemmResidual;
+    g.res_x = x_inout; g.res_xb = xb_out; g.res_ss = ss_out;
+    char msg[256] = "";
+    const int rc = ugk::launch_gemm_tc(g, sms, static_cast<cudaStream_t>(stream), msg, sizeof msg);
+    if (rc != 0) return fail(rc, "ug_gemm_residual_bf16: %s", msg);
+    return UG_OK;
+}
+
 extern "C" int ug_qkv_rope_bf16(const void* a, const void* w_qkv, const void* bias_qkv, void* qkv_out, int M, int K,
                                 int64_t lda, int64_t ldw, int64_t ldo, const float* cos, const float* sin, int L, int Hq, int Hkv,
-                                void* kv_cache_bf16, int cache_L, int cache_row_offset, void* stream)
+                                void* kv_cache_bf16, int cache_L, int cache_row_offset, const float* row_ss, int ss_parts, float rms_eps,
+                                void* stream)
 {
     if (!a || !w_qkv || !qkv_out || !cos || !sin) return fail(UG_ERR_NULL, "ug_qkv_rope_bf16: null pointer");
+    if (row_ss && ss_parts < 1) return fail(UG_ERR_ARG, "ug_qkv_rope_bf16: row_ss needs ss_parts >= 1");
     if (Hq < 1 || Hkv < 1 || L < 1 || M < 1) return fail(UG_ERR_SHAPE, "ug_qkv_rope_bf16: bad shape");
     const int N = (Hq + 2 * Hkv) * 128;
     if (N % 256 || K < 64 || K % 64) return fail(UG_ERR_SHAPE, "ug_qkv_rope_bf16: need (Hq + 2 Hkv) even and K %% 64 == 0 (N=%d K=%d)", N, K);
@@ -333,6 +419,7 @@ extern "C" int ug_qkv_rope_bf16(const void* a, const void* w_qkv, const void* bi
     g.M = M; g.N = N; g.K = K; g.mode = ugk::kGemmQkvRope;
     g.rope_cos = cos; g.rope_sin = sin; g.kv_cache = kv_cache_bf16;
     g.rope_L = L; g.rope_Hq = Hq; g.rope_Hkv = Hkv; g.cache_L = cache_L; g.cache_row0 = cache_row_offset;
+    g.row_ss = row_ss; g.ss_parts = ss_parts; g.rms_eps = rms_eps;
     char msg[256] = "";
     const int rc = ugk::launch_gemm_tc(g, sms, static_cast<cudaStream_t>(stream), msg, sizeof msg);
     if (rc != 0) return fail(rc, "ug_qkv_rope_bf16: %s", msg);

@@ -71,6 +71,20 @@ def best_of_n(model, input_ids_one: torch.Tensor, n_candidates: int, *, topk: in
     (all ids [n, N], all scores [n], indices of the top-k) on every rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if "philox_seed" not in gen_kwargs:
+        # Sharding invariance needs ONE Philox key for the whole prompt: rank 0 draws it (from `generator` if given, else from its
+        # default CUDA generator, which advances) and every rank adopts it -- a rank-local default generator would give each shard
+        # its own stream, and the images would depend on the number of GPUs.
+        gen = gen_kwargs.pop("generator", None)
+        dev = model.device
+        key = torch.zeros(2, dtype=torch.int64, device=dev)
+        if rank == 0:
+            g = gen if gen is not None else torch.cuda.default_generators[dev.index or 0]
+            key = torch.randint(0, 2 ** 62, (2,), generator=g, device=g.device).to(dev)
+        if world > 1:
+            dist.broadcast(key, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        k = key.tolist()
+        gen_kwargs["philox_seed"], gen_kwargs["philox_offset"] = int(k[0]), int(k[1] & 0xFFFFFFFF)
     s, e = shard_range(n_candidates, rank, world)
     batch = input_ids_one.reshape(1, -1).expand(e - s, -1).contiguous()
     ids = model.t2i_generate(input_ids=batch, batch_offset=s, **gen_kwargs)

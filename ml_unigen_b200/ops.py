@@ -29,6 +29,9 @@ def _need_cuda(*ts):
             raise _lib.UnigenB200Error("unigen-b200 kernels need CUDA tensors (there is no CPU path)")
 
 
+DECODE_STEP_LAUNCHES = 2          # decode_fast_kernel + select_kernel (the production path of ug_decode_step_bf16)
+
+
 class DecodeWorkspace:
     """Caller-owned workspace of the decode step (zeroed once; the kernel re-arms it)."""
 
@@ -44,9 +47,11 @@ def decode_step(logits: torch.Tensor, ids_inout: torch.Tensor, *, mask_token_id:
                 sel_prob_out: Optional[torch.Tensor] = None, conf_out: Optional[torch.Tensor] = None,
                 uncond_logits: Optional[torch.Tensor] = None, guidance_scale: float = 0.0,
                 q_noise: Optional[torch.Tensor] = None, u_noise: Optional[torch.Tensor] = None,
-                seed: int = 0, offset: int = 0, batch_offset: int = 0):
+                seed: int = 0, offset: int = 0, batch_offset: int = 0, _debug: Optional[dict] = None):
     """One fused MaskGIT step (models/unigen.py:407-453).  `ids_inout` int64 [B,N] is updated in
-    place; returns (sampled_ids int64 [B,N], masking uint8 [B,N])."""
+    place; returns (sampled_ids int64 [B,N], masking uint8 [B,N]).
+    `_debug` (tests only): dict with rowsum_out / stats tensors, force_exact_bits, exact_kernel -> the call goes through
+    `ugt_decode_step_bf16` (include/unigen_b200_test.h)."""
     _need_cuda(logits, ids_inout)
     if logits.dtype != torch.bfloat16 or logits.dim() != 3 or not logits.is_contiguous():
         raise ValueError("logits must be a contiguous bf16 [B,N,V] tensor")
@@ -66,12 +71,18 @@ def decode_step(logits: torch.Tensor, ids_inout: torch.Tensor, *, mask_token_id:
                        (mask_out, torch.uint8, (B, N))):
         if t is not None and (t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous() or t.device != dev):
             raise ValueError(f"bad optional tensor: expected contiguous {dt} {shp} on {dev}")
-    rc = _lib.lib().ug_decode_step_bf16(
-        _ptr(logits), _ptr(uncond_logits), float(guidance_scale),
-        _ptr(ids_inout), _ptr(sampled_out), _ptr(mask_out), _ptr(sel_prob_out), _ptr(conf_out),
-        _ptr(q_noise), _ptr(u_noise), seed & (2**64 - 1), offset & (2**64 - 1), batch_offset,
-        B, N, V, mask_token_id, int(mask_len_cap), float(temperature),
-        _ptr(workspace.buf), workspace.nbytes, _stream())
+    args = (_ptr(logits), _ptr(uncond_logits), float(guidance_scale),
+            _ptr(ids_inout), _ptr(sampled_out), _ptr(mask_out), _ptr(sel_prob_out), _ptr(conf_out),
+            _ptr(q_noise), _ptr(u_noise), seed & (2**64 - 1), offset & (2**64 - 1), batch_offset,
+            B, N, V, mask_token_id, int(mask_len_cap), float(temperature),
+            _ptr(workspace.buf), workspace.nbytes, _stream())
+    if _debug is None:
+        rc = _lib.lib().ug_decode_step_bf16(*args)
+    else:
+        import ctypes
+        o = _lib.DecodeTestOptions(_ptr(_debug.get("rowsum_out")), int(_debug.get("force_exact_bits", 0)),
+                                   int(bool(_debug.get("exact_kernel", False))), _ptr(_debug.get("stats")))
+        rc = _lib.lib().ugt_decode_step_bf16(*args, ctypes.byref(o))
     _lib.check(rc)
     return sampled_out, mask_out
 
@@ -108,7 +119,8 @@ def export_noise(seed: int, offset: int, B: int, N: int, V: int, device, batch_o
 
 
 def omni_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_len: torch.Tensor,
-                   soi_idx: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None, q_offset: int = 0) -> torch.Tensor:
+                   soi_idx: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None, q_offset: int = 0,
+                   _debug_dump: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Omni attention.  q [B,Lq,Hq,D], k/v [B,L,Hkv,D] bf16 (last dim contiguous, arbitrary other strides);
     pad_len / soi_idx int32 [B].  Query row r is sequence row q_offset + r (Lq = L, q_offset = 0 for the full
     pass; q_offset = soi_idx for the image-block-only pass of the prefix K/V reuse).  Returns out [B,Lq,Hq,D] bf16."""
@@ -125,11 +137,14 @@ def omni_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_len: t
         raise ValueError("pad_len / soi_idx must be int32")
     if out is None:
         out = torch.empty(B, Lq, Hq, D, dtype=torch.bfloat16, device=q.device)
-    rc = _lib.lib().ug_omni_attention_rows_bf16(
-        _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(pad_len), _ptr(soi_idx),
-        B, L, Lq, int(q_offset), Hq, Hkv, D, float(scale),
-        q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
-        out.stride(0), out.stride(1), out.stride(2), _stream())
+    args = (_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(pad_len), _ptr(soi_idx),
+            B, L, Lq, int(q_offset), Hq, Hkv, D, float(scale),
+            q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
+            out.stride(0), out.stride(1), out.stride(2), _stream())
+    if _debug_dump is None:
+        rc = _lib.lib().ug_omni_attention_rows_bf16(*args)
+    else:                                       # tests / tools only (include/unigen_b200_test.h)
+        rc = _lib.lib().ugt_omni_attention_rows_bf16(*args, _ptr(_debug_dump))
     _lib.check(rc)
     return out
 
@@ -186,8 +201,9 @@ def swiglu(gate_up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     return out
 
 
-def embed_rows(table: torch.Tensor, tokens: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """table bf16 [vocab,H], tokens int64 [M] -> fp32 [M,H]."""
+def embed_rows(table: torch.Tensor, tokens: torch.Tensor, out: Optional[torch.Tensor] = None, *, with_norm_operands: bool = False):
+    """table bf16 [vocab,H], tokens int64 [M] -> fp32 [M,H].  With `with_norm_operands` returns (x, xb, ss): also
+    xb = bf16(x) and ss fp32 [M, H/128] = per-128-column sums of x^2, the operands of the norm-folded GEMMs."""
     _need_cuda(table, tokens)
     vocab, H = table.shape
     tokens = tokens.reshape(-1)
@@ -196,8 +212,19 @@ def embed_rows(table: torch.Tensor, tokens: torch.Tensor, out: Optional[torch.Te
     M = tokens.numel()
     if out is None:
         out = torch.empty(M, H, dtype=torch.float32, device=table.device)
-    _lib.check(_lib.lib().ug_embed_rows(_ptr(out), _ptr(table), _ptr(tokens), M, H, vocab, _stream()))
-    return out
+    xb = ss = None
+    if with_norm_operands:
+        xb = torch.empty(M, H, dtype=torch.bfloat16, device=table.device)
+        ss = torch.empty(M, H // 128, dtype=torch.float32, device=table.device)
+    _lib.check(_lib.lib().ug_embed_rows(_ptr(out), _ptr(xb), _ptr(ss), _ptr(table), _ptr(tokens), M, H, vocab, _stream()))
+    return (out, xb, ss) if with_norm_operands else out
+
+
+def norm_operands(x: torch.Tensor):
+    """fp32 [M,H] residual stream -> (xb bf16 [M,H], ss fp32 [M,H/128]) with plain torch ops (host-side helper for
+    callers that hand in their own embeddings; the hot loop gets these from the GEMM / embedding epilogues)."""
+    M, H = x.shape
+    return x.bfloat16(), (x.float() ** 2).view(M, H // 128, 128).sum(-1).contiguous()
 
 
 def cfg_mix_(cond_logits: torch.Tensor, uncond_logits: torch.Tensor, guidance_scale: float) -> torch.Tensor:
@@ -224,10 +251,20 @@ def pack_gate_up(w_gate: torch.Tensor, w_up: torch.Tensor) -> torch.Tensor:
     return torch.stack([w_gate.reshape(I // 128, 128, K), w_up.reshape(I // 128, 128, K)], 1).reshape(2 * I, K).contiguous()
 
 
+def _row_ss_args(row_ss: Optional[torch.Tensor], M: int, eps: float):
+    if row_ss is None:
+        return None, 0, 0.0
+    if row_ss.dtype != torch.float32 or row_ss.dim() != 2 or row_ss.shape[0] != M or not row_ss.is_contiguous():
+        raise ValueError("row_ss must be contiguous fp32 [M, parts]")
+    return row_ss.data_ptr(), int(row_ss.shape[1]), float(eps)
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, mode: int = GEMM_PLAIN,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, row_ss: Optional[torch.Tensor] = None, rms_eps: float = 1e-6) -> torch.Tensor:
     """bf16 a [M,K] x w [N,K]^T on the tcgen05 kernel.  mode GEMM_PLAIN: bf16 [M,N] (+bias);
-    GEMM_SWIGLU: w from `pack_gate_up`, returns bf16 [M,N/2] = silu(gate) * up."""
+    GEMM_SWIGLU: w from `pack_gate_up`, returns bf16 [M,N/2] = silu(gate) * up.
+    `row_ss` fp32 [M, parts]: RMSNorm folding -- row m of the accumulator is scaled by rsqrt(sum(row_ss[m]) / K + rms_eps)
+    (a = bf16(x), the norm gain folded into the columns of w; include/unigen_b200.h)."""
     _need_cuda(a, w, bias)
     if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or a.dim() != 2 or w.dim() != 2:
         raise ValueError("a and w must be 2-D bf16")
@@ -242,14 +279,38 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         out = torch.empty(M, n_out, dtype=torch.bfloat16, device=a.device)
     elif out.shape != (M, n_out) or out.dtype != torch.bfloat16 or out.stride(1) != 1:
         raise ValueError("out must be bf16 [M, n_out] with contiguous rows")
+    ssp, parts, eps = _row_ss_args(row_ss, M, rms_eps)
     _lib.check(_lib.lib().ug_gemm_bf16(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), M, N, K,
-                                       a.stride(0), w.stride(0), out.stride(0), mode, _stream()))
+                                       a.stride(0), w.stride(0), out.stride(0), mode, ssp, parts, eps, _stream()))
     return out
+
+
+def gemm_residual_(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, xb: Optional[torch.Tensor] = None,
+                   ss: Optional[torch.Tensor] = None):
+    """o_proj / down_proj + residual add + statistics of the next RMSNorm in one launch: x fp32 [M,N] += bf16(a w^T) in place;
+    returns (xb bf16 [M,N] = bf16(x), ss fp32 [M, N/128] = per-128-column sums of x^2)."""
+    _need_cuda(a, w, x)
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or a.dim() != 2 or w.dim() != 2 or a.stride(1) != 1 or w.stride(1) != 1:
+        raise ValueError("a and w must be 2-D bf16 with contiguous rows")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or x.dtype != torch.float32 or tuple(x.shape) != (M, N) or not x.is_contiguous():
+        raise ValueError("x must be contiguous fp32 [M, N]; inner dimensions of a and w must agree")
+    if xb is None:
+        xb = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    if ss is None:
+        ss = torch.empty(M, N // 128, dtype=torch.float32, device=a.device)
+    if xb.dtype != torch.bfloat16 or tuple(xb.shape) != (M, N) or not xb.is_contiguous() or ss.dtype != torch.float32 \
+            or tuple(ss.shape) != (M, N // 128) or not ss.is_contiguous():
+        raise ValueError("xb must be contiguous bf16 [M,N], ss contiguous fp32 [M,N/128]")
+    _lib.check(_lib.lib().ug_gemm_residual_bf16(_ptr(a), _ptr(w), _ptr(x), _ptr(xb), _ptr(ss), M, N, K,
+                                                a.stride(0), w.stride(0), _stream()))
+    return xb, ss
 
 
 def qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, bias_qkv: Optional[torch.Tensor], cos: torch.Tensor, sin: torch.Tensor,
              L: int, Hq: int, Hkv: int, kv_cache: Optional[torch.Tensor] = None, cache_row_offset: int = 0,
-             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+             out: Optional[torch.Tensor] = None, row_ss: Optional[torch.Tensor] = None, rms_eps: float = 1e-6) -> torch.Tensor:
     """Fused q/k/v projection + RoPE (+ K/V-cache update): bf16 a [M,K] -> bf16 qkv [M,(Hq+2Hkv)*128] with the q and k
     heads rotated (row m = position m % L; cos/sin fp32 [L,64]); with `kv_cache` (bf16 [M/L, cache_L, 2, Hkv, 128]) the
     rotated k and the v rows also land in cache rows [cache_row_offset, cache_row_offset + L).  One launch instead of
@@ -273,7 +334,8 @@ def qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, bias_qkv: Optional[torch.Tens
         out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
     elif tuple(out.shape) != (M, N) or out.dtype != torch.bfloat16 or out.stride(1) != 1:
         raise ValueError("out must be bf16 [M, (Hq+2Hkv)*128] with contiguous rows")
+    ssp, parts, eps = _row_ss_args(row_ss, M, rms_eps)
     _lib.check(_lib.lib().ug_qkv_rope_bf16(_ptr(a), _ptr(w_qkv), _ptr(bias_qkv), _ptr(out), M, K, a.stride(0), w_qkv.stride(0),
                                            out.stride(0), _ptr(cos), _ptr(sin), L, Hq, Hkv, _ptr(kv_cache), cache_L,
-                                           int(cache_row_offset), _stream()))
+                                           int(cache_row_offset), ssp, parts, eps, _stream()))
     return out

@@ -151,3 +151,21 @@ def smoke_gemm(dev) -> None:
     rel_q = ((qkv[:, : Hq * D].view(B, L, Hq, D).float() - ref_q).norm() / ref_q.norm()).item()
     assert rel_q < 6e-3, f"fused q/k/v + RoPE relative L2 error {rel_q}"
     print(f"smoke: tcgen05 GEMM epilogues: SwiGLU rel-L2 {rel:.2e}, q/k/v + RoPE rel-L2 {rel_q:.2e} vs fp32 formulas")
+    # residual epilogue (o_proj / down_proj + residual add + RMSNorm statistics) and the folded RMSNorm of the consumer GEMM
+    N = 256
+    wd = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16().to(dev)
+    x0 = torch.randn(M, N, generator=g).to(dev)
+    xr = x0.clone()
+    xb, ss = ops.gemm_residual_(x, wd, xr)
+    want = x0 + (x.float() @ wd.float().T).bfloat16().float()
+    e_x = ((xr - want).norm() / want.norm()).item()
+    assert e_x < 2e-3 and torch.equal(xb, xr.bfloat16()), f"residual epilogue: rel-L2 {e_x}"
+    e_ss = ((ss.sum(-1) - xr.pow(2).sum(-1)).abs() / xr.pow(2).sum(-1)).max().item()
+    assert e_ss < 1e-5, f"residual epilogue: row statistics off by {e_ss}"
+    gain = (1 + 0.1 * torch.randn(N, generator=g)).to(dev)
+    wn = (torch.randn(256, N, generator=g) * N ** -0.5).to(dev)
+    got = ops.gemm(xb, (wn * gain[None, :]).bfloat16(), row_ss=ss, rms_eps=1e-6).float()
+    ref = rms_norm(xr, gain, 1e-6) @ wn.T
+    rel_n = ((got - ref).norm() / ref.norm()).item()
+    assert rel_n < 8e-3, f"folded RMSNorm GEMM relative L2 error {rel_n}"
+    print(f"smoke: residual epilogue rel-L2 {e_x:.2e} (xb exact, row sums {e_ss:.1e}); folded RMSNorm + GEMM rel-L2 {rel_n:.2e}")

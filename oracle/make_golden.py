@@ -131,6 +131,89 @@ def make_decode_case(name, *, T, B, N, V, scale, seed, temperature=1.0):
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def make_decode_fullsize(name, *, scale, seed, noise, B=2, N=1024, V=8192, T=18, temperature=1.0):
+    """BASELINE.json's decode shape (N=1024, V=8192, T=18) through the reference's own loop (models/unigen.py:398-455).  Only
+    seeds, sampled ids and masks are stored (75 KB): logits come from `oracle.synthetic_logits_bits` (integer RNG, exact ops),
+    the noise either
+      noise="replay" : from the reference's own generator -- torch.multinomial and gumbel_noise run UNMODIFIED and the test
+                       re-draws exponential_/uniform_ from a clone of `torch.Generator().manual_seed(seed)`; a checksum of the
+                       stream is stored because torch's CPU exponential_ may differ between host CPUs (MKL / libm dispatch), or
+      noise="integer": injected, platform-independent (`oracle.integer_noise`): torch.multinomial(p, 1) is replaced by its
+                       definition `(p / q).argmax(-1)` (probed bit-identical) and gumbel_noise's
+                       uniform_ draw by the injected u; every other line is the reference's."""
+    from oracle import oracle as O
+    ug = ref_loader.load_unigen()
+    smp = sys.modules["models.sampling"]
+    text_vocab = 8
+    vocab = text_vocab + V + 1
+    mask_id = vocab - 1
+    L = 3 + N + 1
+
+    class _Lazy:                                    # per-step full-vocabulary logits, built when the loop asks for them
+        def __init__(self):
+            self.step = 0
+
+        def __call__(self, input_ids=None, input_embeddings=None, attention_mask=None):
+            bits = O.synthetic_logits_bits(seed, self.step, B, N, V, scale)
+            f = torch.zeros(B, L, vocab)
+            f[:, -(N + 1):-1, text_vocab:-1] = torch.from_numpy(bf16_bits_to_f32(bits))
+            self.step += 1
+            return f
+
+    fake = _FakeUniGen(mask_id, None)
+    lazy = _Lazy()
+    fake.__class__ = type("_FakeLazy", (_FakeUniGen,), {"__call__": lambda self, **kw: lazy(**kw)})
+    input_ids = torch.zeros(B, L, dtype=torch.long)
+    input_ids[:, -(N + 1):-1] = mask_id
+    gen = torch.Generator().manual_seed(seed + 100)
+    replay = torch.Generator().manual_seed(seed + 100)
+    rec = dict(sampled_raw=[], masking=[], mask_len=[], q_sum=[], u_sum=[])
+    orig_multinomial, orig_topk, orig_gumbel = torch.multinomial, ug.mask_by_random_topk, smp.gumbel_noise
+    state = {"u": None}
+
+    def multinomial_rec(p, n, generator=None):
+        if noise == "replay":
+            out = orig_multinomial(p, n, generator=generator)
+            q = torch.empty(B * N, V).exponential_(1, generator=replay)
+            assert torch.equal((p / q).argmax(-1), out[:, 0])                 # SURVEY 0-1 on this very call
+            rec["q_sum"].append(O.noise_checksum(q.numpy()))
+        else:
+            q, state["u"] = O.integer_noise(seed, len(rec["sampled_raw"]), B, N, V)
+            out = (p / torch.from_numpy(q).view(B * N, V)).argmax(-1, keepdim=True)
+        rec["sampled_raw"].append(out[:, 0].view(B, N).numpy().astype(np.int16))
+        return out
+
+    def gumbel_injected(t, generator=None):          # sampling.py:24-26 with the draw replaced by the injected tensor
+        return -smp.log(-smp.log(torch.from_numpy(state["u"])))
+
+    def topk_rec(mask_len, probs, temperature=1.0, generator=None):
+        out = orig_topk(mask_len, probs, temperature, generator=generator)
+        rec["mask_len"].append(mask_len.long().view(B).numpy().copy())
+        rec["masking"].append(np.packbits(out.numpy(), axis=-1))
+        if noise == "replay":
+            rec["u_sum"].append(O.noise_checksum(torch.zeros(B, N).uniform_(0, 1, generator=replay).numpy()))
+        return out
+
+    torch.multinomial = multinomial_rec
+    ug.mask_by_random_topk = topk_rec
+    if noise == "integer":
+        smp.gumbel_noise = gumbel_injected
+    try:
+        final = ug.UniGen.t2i_generate(fake, input_ids=input_ids, attention_mask=None, temperature=temperature, timesteps=T,
+                                       guidance_scale=0, noise_schedule=smp.get_mask_chedule("cosine"), generator=gen,
+                                       image_token_num_per_image=N, text_vocab_size=text_vocab)
+    finally:
+        torch.multinomial, ug.mask_by_random_topk, smp.gumbel_noise = orig_multinomial, orig_topk, orig_gumbel
+    if noise == "replay":
+        assert torch.equal(gen.get_state(), replay.get_state()), "generator replay diverged"
+    out = {k: np.stack(v) for k, v in rec.items() if v}
+    path = os.path.join(GOLD, f"decode_full_{name}.npz")
+    np.savez_compressed(path, final_ids=final.numpy().astype(np.int16), mask_token_id=np.int64(mask_id), seed=np.int64(seed),
+                        scale=np.float64(scale), temperature0=np.float64(temperature), shape=np.array([T, B, N, V]),
+                        noise=np.array(noise), **{k: (np.array(v, dtype=np.uint64) if k.endswith("_sum") else v) for k, v in out.items()})
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def make_cfg_case():
     """unigen.py:410 executed by torch on bf16 tensors: guidance_scale * (cond - uncond) + uncond."""
     rng = np.random.default_rng(5)
@@ -204,11 +287,15 @@ if __name__ == "__main__":
     assert ref_loader.available(), "reference tree not mounted"
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["decode", "cfg", "mask", "schedule", "backbone"]
+    which = sys.argv[1:] or ["decode", "cfg", "mask", "schedule", "backbone", "full"]
     if "decode" in which:
         make_decode_case("peaked_v4096", T=4, B=2, N=8, V=4096, scale=4.0, seed=1)
         make_decode_case("flat_v4096", T=4, B=2, N=8, V=4096, scale=0.02, seed=2)
         make_decode_case("peaked_v8192", T=3, B=1, N=16, V=8192, scale=4.0, seed=3)
+    if "full" in which:
+        make_decode_fullsize("peaked_integer", scale=4.0, seed=21, noise="integer")
+        make_decode_fullsize("flat_integer", scale=0.02, seed=22, noise="integer")
+        make_decode_fullsize("unit_replay", scale=1.0, seed=23, noise="replay")
     if "cfg" in which:
         make_cfg_case()
     if "mask" in which:

@@ -100,5 +100,58 @@ def make_backbone_tiny():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def make_t2i_tiny(T: int = 5, B: int = 2, seed: int = 17):
+    """The UNMODIFIED `UniGen.t2i_generate` (models/unigen.py:344-455) end to end on the tiny random-init model: real Qwen2ForCausalLM
+    forward (fp32, sdpa, dense mask), full-vocabulary head, slice, softmax, torch.multinomial, mask_by_random_topk, re-embedding, T
+    steps.  Recorded: per-step sampled ids and masks, final ids, and the noise the reference's generator produced (generator replay,
+    SURVEY.md section 0-7) -- what oracle/t2i_port.py must reproduce."""
+    pu = ref_loader.load_prompting()
+    ug = ref_loader.load_unigen()
+    smp = sys.modules["models.sampling"]
+    vocab = TEXT_VOCAB + V + 1
+    with tempfile.TemporaryDirectory() as d:
+        ref_loader.qwen_config_dir(d, vocab_size=vocab, max_position_embeddings=512,
+                                   **{k: v for k, v in TINY.items() if k != "head_dim"})
+        torch.manual_seed(0)
+        model = ref_loader.build_reference_unigen(d, vocab_size=vocab, codebook_size=V, num_vq_tokens=N_IMG)
+    sd = {("model." + k): torch.from_numpy(v) for k, v in tiny_weights().items()}
+    sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
+    model.llm.load_state_dict(sd, strict=False)
+    ids = torch.from_numpy(tiny_inputs()[0][:B])
+    mask = pu.create_attention_mask_predict_next(ids, pad_id=PAD, soi_id=SOI, eoi_id=EOI, rm_pad_in_image=True)
+    gen = torch.Generator().manual_seed(seed)
+    replay = torch.Generator().manual_seed(seed)
+    rec = dict(sampled_raw=[], masking=[], q=[], u=[])
+    orig_multinomial, orig_topk = torch.multinomial, ug.mask_by_random_topk
+
+    def multinomial_rec(p, n, generator=None):
+        out = orig_multinomial(p, n, generator=generator)
+        rec["sampled_raw"].append(out[:, 0].view(B, N_IMG).numpy().copy())
+        rec["q"].append(torch.empty(B * N_IMG, V).exponential_(1, generator=replay).view(B, N_IMG, V).numpy().copy())
+        return out
+
+    def topk_rec(mask_len, probs, temperature=1.0, generator=None):
+        out = orig_topk(mask_len, probs, temperature, generator=generator)
+        rec["masking"].append(out.numpy().copy())
+        rec["u"].append(torch.zeros(B, N_IMG).uniform_(0, 1, generator=replay).numpy().copy())
+        return out
+
+    torch.multinomial = multinomial_rec
+    ug.mask_by_random_topk = topk_rec
+    try:
+        with torch.no_grad():
+            final = model.t2i_generate(input_ids=ids, attention_mask=mask, temperature=1.0, timesteps=T, guidance_scale=0,
+                                       noise_schedule=smp.get_mask_chedule("cosine"), generator=gen,
+                                       image_token_num_per_image=N_IMG, text_vocab_size=TEXT_VOCAB)
+    finally:
+        torch.multinomial, ug.mask_by_random_topk = orig_multinomial, orig_topk
+    assert torch.equal(gen.get_state(), replay.get_state()), "generator replay diverged"
+    path = os.path.join(ROOT, "tests", "golden", "t2i_tiny.npz")
+    np.savez_compressed(path, ids=ids.numpy(), final_ids=final.numpy(), timesteps=np.int64(T),
+                        **{k: np.stack(v) for k, v in rec.items()})
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     make_backbone_tiny()
+    make_t2i_tiny()

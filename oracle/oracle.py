@@ -154,3 +154,35 @@ def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
 
 def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
     return (b.astype(np.uint32) << 16).view(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# Platform-independent synthetic inputs for the full-size goldens (tests/golden/decode_full_*.npz store only seeds, ids
+# and masks; the test box regenerates logits and noise).  Everything is integer RNG (numpy PCG64 `integers`) followed by
+# exact IEEE operations, so the bits do not depend on libm / MKL / vector ISA of the host.
+# ----------------------------------------------------------------------------------------------
+def synthetic_logits_bits(seed: int, step: int, B: int, N: int, V: int, scale: float) -> np.ndarray:
+    """bf16 bit patterns [B,N,V] of `scale` x an Irwin-Hall(4) variate (approximately N(0,1), |x| <= 3.46)."""
+    rng = np.random.default_rng([int(seed), int(step), 0x10617])
+    s = np.zeros((B, N, V), np.int32)
+    for _ in range(4):
+        s += rng.integers(0, 65536, size=(B, N, V), dtype=np.uint16)
+    x = (s - np.int32(2 * 65535)).astype(np.float32)                       # exact: |value| < 2^18
+    sigma = np.float32(math.sqrt(4.0 * (65536.0 ** 2 - 1.0) / 12.0))
+    return f32_to_bf16_bits(x * np.float32(np.float32(scale) / sigma))     # one float32 multiply, one rounding to bf16
+
+
+def integer_noise(seed: int, step: int, B: int, N: int, V: int):
+    """(q [B,N,V], u [B,N]) float32, exactly representable: k * 2^-24 with k uniform on [1, 2^24).  q stands in for the Exp(1)
+    tensor of torch.multinomial (the contract is `id = argmax p_i / q_i` for whatever q is injected), u for gumbel_noise's."""
+    rng = np.random.default_rng([int(seed), int(step), 0x9015E])
+    q = rng.integers(1, 1 << 24, size=(B, N, V), dtype=np.uint32).astype(np.float32) * np.float32(2.0 ** -24)
+    u = rng.integers(1, 1 << 24, size=(B, N), dtype=np.uint32).astype(np.float32) * np.float32(2.0 ** -24)
+    return q, u
+
+
+def noise_checksum(a: np.ndarray) -> int:
+    """Order-dependent 64-bit checksum of a float32 array's bit patterns (guards generator-replayed noise across hosts)."""
+    w = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64).ravel()
+    idx = (np.arange(w.size, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(32)
+    return int(np.bitwise_xor.reduce(w * (idx | np.uint64(1))) ^ np.uint64(w.size))

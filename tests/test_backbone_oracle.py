@@ -58,6 +58,43 @@ def test_t2i_gen_prompt_layout():
     assert P.tolist() == [0, 5, 99, 50] and S.tolist() == [137] * 4
 
 
+def test_t2i_gen_prompt_matches_reference_class(golden_dir):
+    """tests/golden/prompting.json: recorded from the reference's own UniversalPromptingQwen2 (`__call__(..., 't2i_gen')` ->
+    t2i_gen_prompt, training/prompting_utils.py:113-153, 398-402) on a stub tokenizer (oracle/make_golden_prompting.py): padded,
+    un-padded (max_len None), truncated-with-conv_end and task_token_first cases."""
+    import json
+    from ml_unigen_b200 import prompting
+    cases = json.load(open(os.path.join(golden_dir, "prompting.json")))
+    assert len(cases) >= 5
+    for c in cases:
+        ids, m = prompting.t2i_gen_prompt(c["text_ids"], torch.tensor(c["image_ids"]), conv_start_ids=c["conv_start_ids"],
+                                          conv_end_ids=c["conv_end_ids"], pad_id=c["pad_id"], soi_id=c["soi_id"], eoi_id=c["eoi_id"],
+                                          max_len=c["text_len"], max_seq_len=c["max_seq_len"])
+        assert ids.tolist() == c["input_ids"]
+        assert m.tolist() == c["mask"]
+    # the ids the eval drivers see for the added specials (evaluation/inference_geneval.py:49-52)
+    assert cases[0]["soi_id"] == prompting.QWEN_SOI_ID and cases[0]["eoi_id"] == prompting.QWEN_EOI_ID
+
+
+def test_alternate_schedules_match_reference(golden_dir):
+    """linear / pow / sigmoid schedules (models/sampling.py:53-88) against the values recorded from the reference's own functions
+    (tests/golden/schedule.npz `sched_*`, oracle/make_golden.py `make_schedule`), bit for bit in float32."""
+    from ml_unigen_b200 import sampling
+    g = np.load(os.path.join(golden_dir, "schedule.npz"))
+    names = [k[len("sched_"):] for k in g.files if k.startswith("sched_")]
+    assert sorted(names) == ["linear", "pow0.5", "pow2", "sigmoid"]
+    for name in names:
+        fn = sampling.get_mask_chedule(name)
+        got = np.array([float(fn(torch.tensor(r / 10))) for r in range(1, 11)], np.float32)
+        assert np.array_equal(got.view(np.uint32), g[f"sched_{name}"].view(np.uint32)), name
+    assert sampling.get_mask_chedule("cosine") is sampling.cosine_schedule
+    # cosine: the floor(N * ratio) caps of SURVEY section 0-4, incl. the -1 of the last step
+    caps = [int((1024 * sampling.cosine_schedule(torch.tensor(1.0 * (s + 1) / 18))).floor().item()) for s in range(18)]
+    assert caps == list(g["cap_1024_18"]) and caps[-1] == -1
+    with pytest.raises(ValueError):
+        sampling.get_mask_chedule("nope")
+
+
 def _tiny_torch_weights():
     return {k: torch.from_numpy(v) for k, v in tiny_weights().items()}
 
@@ -98,3 +135,27 @@ def test_oracle_forward_equals_transformers_qwen2():
         ref = m(inputs_embeds=w["embed_tokens.weight"][ids], attention_mask=mask).last_hidden_state
     got = BO.qwen2_forward(w, TINY, w["embed_tokens.weight"][ids], P, S)
     assert (got - ref).abs().max().item() < 1e-4
+
+
+def test_t2i_port_reproduces_the_reference_end_to_end(golden_dir):
+    """oracle/t2i_port.py (the CPU arm of bench.py) against tests/golden/t2i_tiny.npz: the UNMODIFIED UniGen.t2i_generate
+    (models/unigen.py:344-455) on the tiny random-init model, real transformers forward, noise captured by generator replay.
+    Every step's sampled ids and mask and the returned ids must be equal."""
+    from oracle import t2i_port
+    g = np.load(os.path.join(golden_dir, "t2i_tiny.npz"))
+    w = _tiny_torch_weights()
+    T = int(g["timesteps"])
+    ids = torch.from_numpy(g["ids"])
+    for full_head in (True, False):
+        final, recs = t2i_port.t2i_generate_port(
+            w, TINY, ids, image_token_num_per_image=N_IMG, codebook_size=V, text_vocab_size=TEXT_VOCAB,
+            mask_token_id=TEXT_VOCAB + V, pad_id=PAD, soi_id=SOI, timesteps=T, temperature=1.0,
+            q_noise=list(g["q"]), u_noise=list(g["u"]), full_vocab_head=full_head)
+        assert len(recs) == T
+        cur = np.full(g["sampled_raw"][0].shape, TEXT_VOCAB + V, np.int64)
+        for t in range(T):
+            want = np.where(cur == TEXT_VOCAB + V, g["sampled_raw"][t], cur)
+            assert np.array_equal(recs[t]["sampled"], want), f"step {t}"
+            assert np.array_equal(recs[t]["mask"], g["masking"][t]), f"step {t}"
+            cur = np.where(g["masking"][t], TEXT_VOCAB + V, want)
+        assert np.array_equal(final, g["final_ids"])

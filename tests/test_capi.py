@@ -9,10 +9,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "unigen_b200.h")).read()
+def _declared_symbols(header="unigen_b200.h", prefix="ug_"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ug_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_are_exported(built_lib):
@@ -24,8 +24,20 @@ def test_header_symbols_are_exported(built_lib):
     assert set(_lib.SYMBOLS) == set(syms)
 
 
+def test_no_behaviour_switches_in_the_product_abi(built_lib):
+    """Round-1 had thread-local ug_debug_set_* switches in the product header; test instrumentation is now explicit,
+    per call, behind the ugt_ prefix of include/unigen_b200_test.h."""
+    assert not [s for s in _declared_symbols() if "debug" in s]
+    assert not hasattr(built_lib, "ug_debug_set_decode_mode")
+    tsyms = _declared_symbols("unigen_b200_test.h", "ugt_")
+    from ml_unigen_b200 import _lib
+    assert set(tsyms) == set(_lib.TEST_SYMBOLS)
+    for s in tsyms:
+        assert hasattr(built_lib, s)
+
+
 def test_abi_version_and_workspace(built_lib):
-    assert built_lib.ug_abi_version() == 1
+    assert built_lib.ug_abi_version() == 2
     assert built_lib.ug_decode_step_workspace_bytes(16, 1024, 8192) >= 16 * 1024 * 8
     assert built_lib.ug_decode_step_workspace_bytes(0, 1024, 8192) == 0
 

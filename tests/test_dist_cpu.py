@@ -52,3 +52,41 @@ def test_candidate_scores_ignores_known_tokens():
     s = candidate_scores(p)
     assert abs(s[0].item() - (torch.log(torch.tensor(0.5)) + torch.log(torch.tensor(0.25))).item() / 3) < 1e-6
     assert s[1].item() == 0.0
+
+
+class _FakeModel:
+    """Stands in for UniGenB200 on the CPU: every image is a pure function of (philox key, global image index)."""
+    device = torch.device("cpu")
+
+    def t2i_generate(self, input_ids, batch_offset=0, philox_seed=None, philox_offset=0, **kw):
+        n = input_ids.shape[0]
+        idx = torch.arange(batch_offset, batch_offset + n)
+        ids = ((idx[:, None] * 131 + torch.arange(6)[None, :] * 7 + philox_seed % 1000 + philox_offset % 89) % 8192).to(torch.int64)
+        self.last_sel_prob = (0.1 + ((idx[:, None] * 37 + torch.arange(6)[None, :] + philox_seed % 11) % 50).float() / 100)
+        self.seen_key = (philox_seed, philox_offset)
+        return ids
+
+
+def _bon_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ml_unigen_b200 import dist as ugd
+    m = _FakeModel()
+    # every rank hands in its OWN generator state: only rank 0's may decide the stream (sharding invariance)
+    gen = torch.Generator().manual_seed(5 if rank == 0 else 999)
+    ids, scores, top = ugd.best_of_n(m, torch.arange(10), 9, topk=4, generator=gen)
+    ret[rank] = (ids.tolist(), scores.tolist(), top.tolist(), m.seen_key)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_best_of_n_is_invariant_to_the_number_of_ranks():
+    from ml_unigen_b200 import dist as ugd
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bon_worker, args=(2, 31500 + (os.getpid() % 2000), ret), nprocs=2, join=True)
+    assert ret[0] == ret[1]                                   # same gathered result and the same Philox key on both ranks
+    m = _FakeModel()                                          # the single-process run with rank 0's generator
+    ids, scores, top = ugd.best_of_n(m, torch.arange(10), 9, topk=4, generator=torch.Generator().manual_seed(5))
+    assert (ids.tolist(), scores.tolist(), top.tolist(), m.seen_key) == ret[0]

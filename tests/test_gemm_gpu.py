@@ -173,3 +173,99 @@ def test_gemm_shape_sweep_against_cublas():
                 unf = ops.swiglu(F.linear(a, w))
                 assert ((act.float() - unf.float()).abs().max().item()) <= 2 ** -6 * max(unf.float().abs().max().item(), 1e-3), (M, N, K)
     print(f"{n_equal} of 36 plain outputs bit-identical to cuBLAS")      # informational: depends on cuBLAS' kernel choice
+
+
+# ------------------------------------------------------------------------------------------------------------
+# round 2: o_proj / down_proj + residual add + RMSNorm statistics in one launch; RMSNorm folded into the consumer GEMMs
+@pytest.mark.parametrize("M,N,K", [(300, 512, 1536), (2082, 1536, 8960), (16 * 1026, 1536, 1536), (37, 256, 192), (129, 1536, 64),
+                                   (700, 256, 512), (9000, 768, 512)])
+def test_gemm_residual_epilogue(M, N, K):
+    """ug_gemm_residual_bf16: x += bf16(a w^T), xb = bf16(x), ss = per-128-column sums of x^2.  The accumulator is the plain
+    mode's, so x must equal x0 + float(ops.gemm(a, w)) BIT FOR BIT; xb is its bf16 rounding exactly; ss is an fp32 sum
+    (different order from torch's: 1e-5 relative).  Covers the split-tail rounds and ragged last m blocks."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    x0 = torch.randn(M, N, device=dev, generator=g) * 3
+    x = x0.clone()
+    guard = torch.full((64,), 7.0, device=dev)                  # allocated right behind: a write past row M would show
+    xb, ss = ops.gemm_residual_(a, w, x)
+    want = x0 + ops.gemm(a, w).float()
+    assert torch.equal(x, want)
+    assert torch.equal(xb, want.bfloat16())
+    ref_ss = (want.double() ** 2).view(M, N // 128, 128).sum(-1)
+    assert ((ss.double() - ref_ss).abs() <= 1e-5 * ref_ss + 1e-12).all()
+    assert torch.equal(guard, torch.full((64,), 7.0, device=dev))
+    # a second application accumulates on top (in-place semantics)
+    xb2, ss2 = ops.gemm_residual_(a, w, x, xb, ss)
+    assert xb2.data_ptr() == xb.data_ptr() and torch.equal(x, want + ops.gemm(a, w).float())
+
+
+@pytest.mark.parametrize("M,K", [(300, 1536), (16 * 130, 1536), (777, 256)])
+def test_rmsnorm_folding_matches_unfused_norm_then_gemm(M, K):
+    """(g x / rms) W^T == (1/rms) (bf16(x) (W diag g)^T): the three consumer epilogues with `row_ss` against the unfused sequence
+    ug_add_rmsnorm -> GEMM and against the fp32 formula.  The rounding points move (x is rounded to bf16 before the scaling
+    instead of after, the weights carry the gain), so the two bf16 paths differ by rounding noise; both are held to the same
+    bound against fp32: relative L2 <= 6e-3 (plain / q/k/v), 1e-2 (SwiGLU)."""
+    from oracle import backbone_oracle as BO
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + K)
+    eps = 1e-6
+    x = torch.randn(M, K, device=dev, generator=g) * (0.5 + 4 * torch.rand(M, 1, device=dev, generator=g))   # rows of different scale
+    gain = (1 + 0.2 * torch.randn(K, device=dev, generator=g)).bfloat16()
+    xb, ss = ops.norm_operands(x)
+    h_ref32 = gain.float() * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))
+    h_unf = ops.add_rmsnorm(x.clone(), gain, eps)
+    fold = lambda w: (w.float() * gain.float()[None, :]).bfloat16()
+    rel = lambda got, ref: ((got.float() - ref).norm() / ref.norm()).item()
+    # plain (+bias): the codebook head
+    N = 512
+    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, device=dev, generator=g).bfloat16()
+    ref = F.linear(h_ref32, w.float(), b.float())
+    got = ops.gemm(xb, fold(w), b, row_ss=ss, rms_eps=eps)
+    unf = ops.gemm(h_unf, w, b)
+    print(f"plain: folded {rel(got, ref):.2e}  unfused {rel(unf, ref):.2e}")
+    assert rel(got, ref) <= 6e-3 and rel(unf, ref) <= 6e-3
+    # SwiGLU
+    I = 384
+    wg = (torch.randn(I, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    wu = (torch.randn(I, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    ref = F.silu(F.linear(h_ref32, wg.float())) * F.linear(h_ref32, wu.float())
+    got = ops.gemm(xb, ops.pack_gate_up(fold(wg), fold(wu)), mode=ops.GEMM_SWIGLU, row_ss=ss, rms_eps=eps)
+    unf = ops.gemm(h_unf, ops.pack_gate_up(wg, wu), mode=ops.GEMM_SWIGLU)
+    print(f"SwiGLU: folded {rel(got, ref):.2e}  unfused {rel(unf, ref):.2e}")
+    assert rel(got, ref) <= 1e-2 and rel(unf, ref) <= 1e-2
+    # q/k/v + RoPE
+    if M % 3 == 0:
+        B, L, Hq, Hkv, D = 3, M // 3, 2, 1, 128
+        wq = (torch.randn((Hq + 2 * Hkv) * D, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+        bq = torch.randn((Hq + 2 * Hkv) * D, device=dev, generator=g).bfloat16()
+        cos, sin = BO.rope_cos_sin(L, D, 1e6, dev)
+        ch, sh = cos[:, : D // 2].contiguous(), sin[:, : D // 2].contiguous()
+        got = ops.qkv_rope(xb, fold(wq), bq, ch, sh, L, Hq, Hkv, row_ss=ss, rms_eps=eps)
+        unf = ops.qkv_rope(h_unf, wq, bq, ch, sh, L, Hq, Hkv)
+        full = F.linear(h_ref32, wq.float(), bq.float())
+        ref_q = BO.apply_rope(full[:, : Hq * D].view(B, L, Hq, D), cos, sin)
+        gq = got[:, : Hq * D].view(B, L, Hq, D)
+        uq = unf[:, : Hq * D].view(B, L, Hq, D)
+        print(f"q/k/v: folded {rel(gq, ref_q):.2e}  unfused {rel(uq, ref_q):.2e}")
+        assert rel(gq, ref_q) <= 6e-3 and rel(uq, ref_q) <= 6e-3
+        assert rel(got[:, (Hq + Hkv) * D:], full[:, (Hq + Hkv) * D:]) <= 6e-3
+
+
+def test_embed_rows_norm_operands():
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(3)
+    H = 1536
+    table = torch.randn(5000, H, device=dev, generator=g).bfloat16()
+    tok = torch.randint(0, 5000, (4, 97), device=dev, generator=g)
+    x, xb, ss = ops.embed_rows(table, tok, with_norm_operands=True)
+    assert torch.equal(x, table[tok.reshape(-1)].float()) and torch.equal(xb, table[tok.reshape(-1)])
+    ref = (x.double() ** 2).view(-1, H // 128, 128).sum(-1)
+    assert ((ss.double() - ref).abs() <= 1e-5 * ref).all()
+    assert torch.equal(ops.embed_rows(table, tok), x)

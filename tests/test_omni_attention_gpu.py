@@ -75,12 +75,8 @@ def test_omni_attention_matches_fp32_reference(dev, B, L, P, S):
     Pt = torch.tensor(P, dtype=torch.int32, device=dev)
     St = torch.tensor(S, dtype=torch.int32, device=dev)
     dump = torch.zeros(2 * 128 * 128 + 2048, dtype=torch.float32, device=dev)
-    _lib.lib().ug_debug_set_attn_dump(dump.data_ptr())
-    try:
-        out = ops.omni_attention(q, k, v, Pt, St, D ** -0.5)
-        torch.cuda.synchronize()
-    finally:
-        _lib.lib().ug_debug_set_attn_dump(None)
+    out = ops.omni_attention(q, k, v, Pt, St, D ** -0.5, _debug_dump=dump)
+    torch.cuda.synchronize()
     ref = BO.attention_ref(q, k, v, Pt, St, D ** -0.5)
     # pad rows (i < P_b) are computed (causal among pads) but unused by the model; they are checked too
     try:

@@ -3,7 +3,7 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from ml_unigen_b200 import ops, _lib
+from ml_unigen_b200 import ops
 dev = torch.device("cuda:0")
 B, L, Hq, Hkv, D = 16, 1163, 12, 2, 128
 g = torch.Generator(device=dev).manual_seed(0)
@@ -15,10 +15,8 @@ S = torch.full((B,), 137, dtype=torch.int32, device=dev)
 for _ in range(3):
     ops.omni_attention(q, k, v, P, S, D ** -0.5)
 dump = torch.zeros(32768 + 2048, dtype=torch.float32, device=dev)
-_lib.lib().ug_debug_set_attn_dump(dump.data_ptr())
-ops.omni_attention(q, k, v, P, S, D ** -0.5)
+ops.omni_attention(q, k, v, P, S, D ** -0.5, _debug_dump=dump)
 torch.cuda.synchronize()
-_lib.lib().ug_debug_set_attn_dump(None)
 t = dump[32768:].cpu().view(4, 64, 8)
 names = {0: "softmaxA", 1: "softmaxB", 2: "mma"}
 for role in (0, 1):

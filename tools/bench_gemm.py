@@ -33,14 +33,14 @@ def main():
     ap.add_argument("--m", type=int, default=16 * 1026)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default="gpurun_out/gemm_bench.json")
-    ap.add_argument("--shapes", default="gate_up,qkv,o,down,head,qkv_rope")
+    ap.add_argument("--shapes", default="gate_up,qkv_rope,head,o_res,down_res,o,down")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
     M = a.m
     shapes = {"gate_up": (17920, 1536, "swiglu"), "qkv": (2048, 1536, "bias"), "o": (1536, 1536, "plain"),
               "down": (1536, 8960, "plain"), "head": (8192, 1536, "plain"),
-              "qkv_rope": (2048, 1536, "rope")}
+              "qkv_rope": (2048, 1536, "rope"), "o_res": (1536, 1536, "residual"), "down_res": (1536, 8960, "residual")}
     res = []
     for name in a.shapes.split(","):
         N, K, kind = shapes[name]
@@ -76,6 +76,24 @@ def main():
             t_lin = timed(lambda i: F.linear(x, ws[i % ncopies], bias), a.iters)
             t_own = timed(lambda i: ops.qkv_rope(x, ws[i % ncopies], bias, cos, sin, L, 12, 2, kv_cache=caches[1], out=out_p), a.iters)
             t_own_plain = timed(lambda i: ops.gemm(x, ws[i % ncopies], bias, out=out_p), a.iters)
+        elif kind == "residual":
+            # round 2: o_proj / down_proj + residual add + RMSNorm statistics in ONE launch, against what round 1 ran:
+            # cuBLAS GEMM + ug_add_rmsnorm (add, write x back, normalise, write h)
+            gain = torch.ones(N, dtype=torch.bfloat16, device=dev)
+            xs = torch.randn(M, N, device=dev, generator=g)
+            x_own, x_ref = xs.clone(), xs.clone()
+            xb = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            ss = torch.empty(M, N // 128, dtype=torch.float32, device=dev)
+            h = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            ops.gemm_residual_(x, ws[0], x_own, xb, ss)
+            ops.add_rmsnorm(x_ref, gain, 1e-6, F.linear(x, ws[0]), out=h)
+            got, ref = x_own.bfloat16(), x_ref.bfloat16()
+            ref32 = xs[:512] + F.linear(x[:512].float(), ws[0].float())
+            t_ref = timed(lambda i: ops.add_rmsnorm(x_ref, gain, 1e-6, F.linear(x, ws[i % ncopies]), out=h), a.iters)
+            t_lin = timed(lambda i: F.linear(x, ws[i % ncopies]), a.iters)
+            t_own = timed(lambda i: ops.gemm_residual_(x, ws[i % ncopies], x_own, xb, ss), a.iters)
+            out_p = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            t_own_plain = timed(lambda i: ops.gemm(x, ws[i % ncopies], out=out_p), a.iters)
         else:
             ref = F.linear(x, ws[0], bias)
             got = ops.gemm(x, ws[0], bias)

@@ -1,5 +1,4 @@
-"""In-loop timing of every GEMM of the step (CUDA events inside two full generations), for UG_PLAIN_GEMM=cublas|own:
-are the plain GEMMs themselves slower inside the power-capped loop, or do they slow their neighbours down?"""
+"""In-loop timing of every GEMM and attention launch of the step (CUDA events inside two full generations, eager)."""
 import json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,7 +24,7 @@ e1.record()
 torch.cuda.synchronize()
 M = 16 * 1026
 avg = lambda xs: sum(xs) / max(len(xs), 1)
-res = dict(mode=os.environ.get("UG_PLAIN_GEMM", "cublas"), ms_per_generation=e0.elapsed_time(e1) / 2,
+res = dict(mode="own kernels only (residual epilogues, folded RMSNorm)", ms_per_generation=e0.elapsed_time(e1) / 2,
            gate_up=avg([a.elapsed_time(b) for a, b, m in bb.mlp_events if m == M]),
            attention=avg([a.elapsed_time(b) for a, b, lq in bb.attn_events if lq == 1026]),
            down=avg([a.elapsed_time(b) for a, b, m, k in bb.plain_events if m == M and k == 8960]),
