@@ -35,6 +35,13 @@
 
 #include "gemm_tc.h"
 
+#ifndef UG_RES_DEBUG
+#define UG_RES_DEBUG 0         // timing experiments only: 1 no x loads, 2 no x / xb stores, 4 no second pass at all
+#endif
+#ifndef UG_RES_PREFETCH
+#define UG_RES_PREFETCH 0      // residual epilogue, L2 prefetch of the x tile: 0 none, 1 one bulk request per row, 2 four 2-D tensor requests
+#endif
+
 namespace ugk {
 namespace {
 
@@ -120,9 +127,15 @@ __device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes)
                  "r"(bytes)
                  : "memory");
 }
+// Arrive on a barrier of the leader CTA.  What the arrival hands over is a TMEM accumulator buffer whose reads (tcgen05.ld +
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync) have completed in this thread -- no global or shared-memory data -- so a
+// RELAXED arrive is sufficient.  A releasing arrive compiles to a memory barrier (cluster scope: MEMBAR.ALL.GPU, the default CTA
+// scope: MEMBAR.ALL.CTA) that first drains every outstanding global store of the thread: harmless next to TMA stores, but with
+// the plain x / xb stores of the residual epilogue it was the hottest line of the kernel (28 % of the stall samples,
+// profiles/r2_ncu_gemm_residual.md).
 __device__ __forceinline__ void bar_arrive_cluster(uint32_t cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity)
 {
@@ -239,6 +252,10 @@ __device__ __forceinline__ float row_rstd(const GemmParams& p, int m)
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_tensor(const CUtensorMap* map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -394,10 +411,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
             const float rstd = row_rstd(p, m0 + r);
             if (MODE == kGemmResidual) {
-                // the x tile this CTA is about to read-modify-write: into L2 while the MMAs of the unit still run
-                const int et = (int)threadIdx.x - 128, prow = m0 + (et & 127), ph = et >> 7;
-                if (prow < p.M && (half < 0 || ph == half))
-                    prefetch_l2_bulk(p.res_x + (int64_t)prow * p.N + nb * kGN + ph * 128, 512u);
+                // The x tile a unit read-modify-writes is pulled into L2 ONE UNIT AHEAD (the first one at kernel start): when the
+                // epilogue is the longer half of the pipeline the accumulator is already waiting, so a prefetch issued here for
+                // the tile of THIS unit has no lead time (measured: no effect), and the 16 x 512 B a warp keeps in flight per batch
+                // cannot hide DRAM latency (o_proj + residual was latency-bound at 2.4 TB/s of loads).
+                auto prefetch_unit = [&](int uj) {
+                    int mb2, nb2, half2;
+                    unit(uj, mb2, nb2, half2);
+                    const int pm0 = mb2 * 256 + (int)rank * kGM;
+#if UG_RES_PREFETCH == 1
+                    const int et = (int)threadIdx.x - 128, prow = pm0 + (et & 127), ph = et >> 7;
+                    if (prow < p.M && (half2 < 0 || ph == half2))
+                        prefetch_l2_bulk(p.res_x + (int64_t)prow * p.N + nb2 * kGN + ph * 128, 512u);
+#elif UG_RES_PREFETCH == 2
+                    if (issuer && pm0 < p.M) {     // tm_o describes x (fp32 [M, N], boxes of 128 rows x 64 columns) in this mode
+                        const int c0 = nb2 * kGN + (half2 > 0 ? 128 : 0), nbox = half2 < 0 ? 4 : 2;
+                        for (int i = 0; i < nbox; ++i) prefetch_l2_tensor(&tm_o, c0 + 64 * i, pm0);
+                    }
+#endif
+                };
+                if (ui == 0) prefetch_unit(0);
+                if (ui + 1 < n_units) prefetch_unit(ui + 1);
             }
             bar_wait(&bars->acc_full[as], aph);
             tc_fence_after();
@@ -574,13 +608,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         const uint32_t lane_off = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(lane & 1) * 8u;
                         const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
 #pragma unroll
-                        for (int bch = 0; bch < 2; ++bch) {
+                        for (int bch = 0; bch < ((UG_RES_DEBUG & 4) ? 0 : 2); ++bch) {
                             float4 xv[8];
+                            float sq[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int row = w8 * 16 + bch * 8 + i;
                                 xv[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                                if (m0 + row < p.M)
+                                if (m0 + row < p.M && !(UG_RES_DEBUG & 1))
                                     xv[i] = *reinterpret_cast<const float4*>(p.res_x + (int64_t)(m0 + row) * p.N + col0 + lane * 4);
                             }
 #pragma unroll
@@ -593,19 +628,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                                 y.y = xv[i].y + bf16hi(d.x);
                                 y.z = xv[i].z + bf16lo(d.y);
                                 y.w = xv[i].w + bf16hi(d.y);
-                                float sq = y.x * y.x;
-                                sq = fmaf(y.y, y.y, sq);
-                                sq = fmaf(y.z, y.z, sq);
-                                sq = fmaf(y.w, y.w, sq);
-#pragma unroll
-                                for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
-                                if (m0 + row < p.M) {
+                                float q2 = y.x * y.x;
+                                q2 = fmaf(y.y, y.y, q2);
+                                q2 = fmaf(y.z, y.z, q2);
+                                sq[i] = fmaf(y.w, y.w, q2);
+                                if (m0 + row < p.M && (!(UG_RES_DEBUG & 2) || y.x == 12345.678f)) {
                                     const int64_t gi = (int64_t)(m0 + row) * p.N + col0 + lane * 4;
                                     *reinterpret_cast<float4*>(p.res_x + gi) = y;
                                     *reinterpret_cast<uint2*>(p.res_xb + gi) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
-                                    if (lane == 0) p.res_ss[(int64_t)(m0 + row) * (p.N >> 7) + (col0 >> 7)] = sq;
                                 }
                             }
+                            // the 8 row sums of the batch in 9 shuffles instead of 40: a butterfly that halves the number of
+                            // rows a lane carries at every step (bits 4, 3, 2 of the lane index pick the row), then the last two
+                            // steps on the single remaining value.  Every row is summed by the same tree: deterministic.
+                            float s4[4], s2[2];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float keep = (lane & 16) ? sq[j + 4] : sq[j], send = (lane & 16) ? sq[j] : sq[j + 4];
+                                s4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const float keep = (lane & 8) ? s4[j + 2] : s4[j], send = (lane & 8) ? s4[j] : s4[j + 2];
+                                s2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                            }
+                            float s1 = ((lane & 4) ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? s2[0] : s2[1], 4);
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                            const int ri = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                            const int srow = m0 + w8 * 16 + bch * 8 + ri;
+                            if ((lane & 3) == 0 && srow < p.M) p.res_ss[(int64_t)srow * (p.N >> 7) + (col0 >> 7)] = s1;
                         }
                     } else {
                         fence_async_smem();
@@ -649,6 +701,19 @@ EncodeTiledFn get_encode_fn()
 }
 
 // row-major bf16 [rows, cols] with row stride ld elements; box = [box_rows x 64 cols], 128-byte swizzle
+// row-major fp32 [rows, cols] (contiguous rows), boxes of 128 rows x 64 columns, no swizzle: only used to PREFETCH tiles of the
+// residual stream into L2 (cp.async.bulk.prefetch.tensor), never to move them into shared memory
+bool make_map_2d_f32(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t rows, int64_t cols)
+{
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool make_map_2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows = 128)
 {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -679,7 +744,7 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     if (g.row_ss && g.ss_parts < 1) { snprintf(msg, msg_len, "gemm: row_ss needs ss_parts >= 1"); return -4; }
     if (!make_map_2d(enc, &ta, g.a, g.M, g.K, g.lda) || !make_map_2d(enc, &tw, g.w, g.N, g.K, g.ldw) ||
         !make_map_2d(enc, &twh, g.w, g.N, g.K, g.ldw, 64) ||
-        !(residual ? make_map_2d(enc, &to, g.a, g.M, g.K, g.lda) : make_map_2d(enc, &to, g.out, g.M, n_out, g.ldo))) {
+        !(residual ? make_map_2d_f32(enc, &to, g.res_x, g.M, g.N) : make_map_2d(enc, &to, g.out, g.M, n_out, g.ldo))) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled rejected the a/w/out layout");
         return -3;
     }

@@ -239,6 +239,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 #ifndef UG_ATTN_POLY
 #define UG_ATTN_POLY 0       // of every 4 pairs of exponentials, how many go to the FMA pipe (polynomial); 0 = all on MUFU
 #endif
+#ifndef UG_ATTN_QK128
+#define UG_ATTN_QK128 1      // 1: S_x = Q_x K_t^T as ONE N = 128 MMA per k step (8 KB of operands per 64 cycles of math); 0: round 1's two
+#endif                       //    N = 64 halves (6 KB per 32 cycles: shared-memory bound, ~52 cycles each -- the MMA warp paced the kernel)
 #ifndef UG_ATTN_TURNS
 #define UG_ATTN_TURNS 0      // 1: the two softmax warpgroups alternate (named barriers), 0: free running
 #endif
@@ -499,27 +502,28 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         // softmax warps and the tensor core both stay busy.  Slot order per kv tile: (A,0) (B,0) (A,1) (B,1); in
         // each slot: O_x += P_x[half] V_t[half]  then  S_x[half] = Q_x K_(t+1)[half]^T.
         {
-            constexpr uint32_t idesc_qk = make_idesc(kBM, 64, 0, 0);        // S half: M=128, N=64
+            constexpr uint32_t idesc_qk = make_idesc(kBM, UG_ATTN_QK128 ? kBN : 64, 0, 0);      // S tile (or half): M=128, N=128 (64)
             constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);        // O:      M=128, N=128, K=64 per half
             const uint32_t qa_addr = s_u32(smem + kOff2QA), qb_addr = s_u32(smem + kOff2QB);
             int np[2][2] = {{0, 0}, {0, 0}};                 // P halves consumed (phase of p_full)
             bool o_started[2] = {false, false};
             const uint32_t q_lo[2] = {desc_lo_kmajor(qa_addr), desc_lo_kmajor(qb_addr)};
             const uint32_t k_lo0 = desc_lo_kmajor(s_u32(smem + kOff2K)), v_lo0 = desc_lo_mnmajor(s_u32(smem + kOff2V));
+            auto tile_on = [&](int x, int t) { return half_on(x, t, 0) || half_on(x, t, 1); };
+            // scores of kv tile t for query tile x: the whole 128-column tile (hf < 0) or one 64-column half
             auto issue_qk = [&](int x, int t, int hf) {
                 const int j = t - tU0, s = j % kKVStages;
                 // K tile: two 64-wide d panels of [128 kv rows x 128 B]; kv rows 64*hf.. start 8 KB into each panel
-                const uint32_t kl = k_lo0 + (uint32_t)s * (kTileBytes >> 4) + (uint32_t)hf * ((64u * 128u) >> 4);
+                const uint32_t kl = k_lo0 + (uint32_t)s * (kTileBytes >> 4) + (uint32_t)(hf > 0 ? 1 : 0) * ((64u * 128u) >> 4);
                 const uint32_t ql = q_lo[x];
-                const uint32_t d = tmem + (uint32_t)x * 128u + (uint32_t)hf * 64u;
+                const uint32_t d = tmem + (uint32_t)x * 128u + (uint32_t)(hf > 0 ? 1 : 0) * 64u;
 #pragma unroll
                 for (int k = 0; k < kD / 16; ++k) {
                     // 16 bf16 along d = 32 bytes inside the 128-byte swizzle row; panel switch at k = 4
-                    constexpr uint32_t dummy = 0; (void)dummy;
                     const uint32_t off = (uint32_t)(k >> 2) * (kPanelBytes >> 4) + (uint32_t)(k & 3) * 2u;
                     tc_mma_ss_lo(d, ql + off, kl + off, idesc_qk, k > 0 ? 1u : 0u);
                 }
-                tc_commit(&bars->s_full[x][hf]);
+                tc_commit(&bars->s_full[x][hf > 0 ? 1 : 0]);
             };
             auto wait_k = [&](int t) {
                 const int j = t - tU0, s = j % kKVStages;
@@ -533,9 +537,14 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             bar_wait(&bars->q_full, 0);
             {   // prologue: scores of the first kv tile
                 const int s = wait_k(tU0);
-                for (int hf = 0; hf < 2; ++hf)
+                if (UG_ATTN_QK128) {
                     for (int x = 0; x < 2; ++x)
-                        if (half_on(x, tU0, hf)) issue_qk(x, tU0, hf);
+                        if (tile_on(x, tU0)) issue_qk(x, tU0, -1);
+                } else {
+                    for (int hf = 0; hf < 2; ++hf)
+                        for (int x = 0; x < 2; ++x)
+                            if (half_on(x, tU0, hf)) issue_qk(x, tU0, hf);
+                }
                 tc_commit(&bars->k_empty[s]);
             }
             for (int t = tU0; t < tU1; ++t) {
@@ -566,7 +575,16 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                             if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 2);
                             if (last_pv(x, t, hf)) tc_commit(&bars->o_done[x]);
                         }
-                        if (next && half_on(x, t + 1, hf)) {
+                        if (UG_ATTN_QK128) {
+                            // the whole next S_x tile overwrites both P halves of this one: it goes behind the LAST P V of (x, t)
+                            // (the tensor pipe executes in issue order); a tile without work yields its turn in the second half
+                            const bool last_here = half_on(x, t, 1) ? hf == 1 : (half_on(x, t, 0) ? hf == 0 : hf == 1);
+                            if (next && last_here && tile_on(x, t + 1)) {
+                                if (!k_ready) { sn = wait_k(t + 1); k_ready = true; }
+                                issue_qk(x, t + 1, -1);
+                                if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 3);
+                            }
+                        } else if (next && half_on(x, t + 1, hf)) {
                             if (!k_ready) { sn = wait_k(t + 1); k_ready = true; }
                             issue_qk(x, t + 1, hf);
                             if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 3);
@@ -610,10 +628,14 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             float l_run = 0.0f;
             const bool dump = p.dbg && x == 0 && qp == 0 && h == 0 && b == 0;
 
-            int ns[2] = {0, 0};                           // halves processed (phase of s_full)
+            int ns[2] = {0, 0};                           // halves (QK128: tiles, in ns[0]) processed (phase of s_full)
             int n_pub = 0;                                // P halves published so far by this warpgroup
             bool o_live = false;                          // O_x holds (or is about to hold) an accumulation
             for (int t = t0; t < t1; ++t) {
+              if (UG_ATTN_QK128 && (half_on(x, t, 0) || half_on(x, t, 1))) {      // the scores of the whole tile land at once
+                  bar_wait(&bars->s_full[x][0], (uint32_t)ns[0] & 1u);
+                  ++ns[0];
+              }
               for (int hf = 0; hf < 2; ++hf) {
                 if (!half_on(x, t, hf)) continue;
                 const int n = 2 * (t - t0) + hf;
@@ -622,8 +644,10 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 const int clo = lo - j0, chi = hi - j0;
                 const uint32_t sh_addr = s_addr + (uint32_t)hf * 64u;
                 if (r == 0) UG_TL(x, n, 0);
-                bar_wait(&bars->s_full[x][hf], (uint32_t)ns[hf] & 1u);
-                ++ns[hf];
+                if (!UG_ATTN_QK128) {
+                    bar_wait(&bars->s_full[x][hf], (uint32_t)ns[hf] & 1u);
+                    ++ns[hf];
+                }
                 tc_fence_after();
                 if (r == 0) UG_TL(x, n, 1);
                 // 64 scores of this row come to registers: two loads in flight, one wait

@@ -37,6 +37,8 @@ def omni_b200(module, query, key, value, attention_mask, dropout=0.0, scaling=No
     if scaling is None:
         scaling = query.shape[-1] ** -0.5
     q, k, v = (t.transpose(1, 2).to(torch.bfloat16) for t in (query, key, value))     # strided views: consumed without a copy
+    if k.stride() != v.stride():      # transformers hands over a rotated (new, [B,H,L,D]-contiguous) key and a projection view as value;
+        k, v = k.contiguous(), v.contiguous()          # the C ABI takes ONE set of k/v strides
     out = ops.omni_attention(q, k, v, P.contiguous(), S.contiguous(), float(scaling))
     return out.to(query.dtype), None
 

@@ -131,8 +131,8 @@ def omni_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_len: t
         raise ValueError("q, k, v must be bf16")
     if q.stride(3) != 1 or k.stride(3) != 1 or v.stride(3) != 1:
         raise ValueError("head_dim must be contiguous")
-    if k.stride() != v.stride() or k.shape != v.shape:
-        raise ValueError("k and v must share shape and strides")
+    if k.shape != v.shape or any(sk != sv for sk, sv, n in zip(k.stride(), v.stride(), k.shape) if n > 1):
+        raise ValueError("k and v must share shape and strides")           # (the stride of a size-1 dimension is immaterial)
     if pad_len.dtype != torch.int32 or soi_idx.dtype != torch.int32:
         raise ValueError("pad_len / soi_idx must be int32")
     if out is None:
