@@ -240,7 +240,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 #define UG_ATTN_POLY 0       // of every 4 pairs of exponentials, how many go to the FMA pipe (polynomial); 0 = all on MUFU
 #endif
 #ifndef UG_ATTN_QK128
-#define UG_ATTN_QK128 1      // 1: S_x = Q_x K_t^T as ONE N = 128 MMA per k step (8 KB of operands per 64 cycles of math); 0: round 1's two
+#define UG_ATTN_QK128 0      // 1: S_x = Q_x K_t^T as ONE N = 128 MMA per k step (8 KB of operands per 64 cycles of math); 0: round 1's two
 #endif                       //    N = 64 halves (6 KB per 32 cycles: shared-memory bound, ~52 cycles each -- the MMA warp paced the kernel)
 #ifndef UG_ATTN_TURNS
 #define UG_ATTN_TURNS 0      // 1: the two softmax warpgroups alternate (named barriers), 0: free running
@@ -347,9 +347,17 @@ constexpr uint32_t kOff2QB = kOff2QA + kTileBytes;
 constexpr uint32_t kOff2K = kOff2QB + kTileBytes;
 constexpr uint32_t kOff2V = kOff2K + kKVStages * kTileBytes;
 constexpr uint32_t kOff2Bar = kOff2V + kKVStages * kTileBytes;
-constexpr uint32_t kAttn2Smem = kOff2Bar + 256 + 1024;
+constexpr uint32_t kOff2Items = kOff2Bar + 512;
+constexpr uint32_t kAttn2Smem = kOff2Items + 32 * 80 + 1024;
 constexpr int kAttn2Threads = 320;           // 2 softmax warpgroups (one per query tile) + TMA warp + MMA warp
 constexpr float kStaleSum = 65536.0f;         // a 64-column row sum above this means the softmax reference lags the scores by > ~10 bits
+
+struct ItemInfo {                 // one work item of the persistent grid, decoded once per CTA (see the kernel)
+    unsigned long long hmask[2];
+    int h, b, qp, lA, R, P, S;
+    int tA0, tA1, tB0, tB1, tU0, tU1, kv_off, flags;       // flags: 1 packed tail tile, 2 has tile B, 4 nothing to do
+};
+constexpr int kItemTable = 32;
 
 struct Attn2Bars {
     uint64_t q_full;
@@ -359,11 +367,21 @@ struct Attn2Bars {
     uint64_t p_full[2][2];       // [tile][half]: 64 probability columns written to TMEM by the 128 softmax threads
     uint64_t pv_done[2];         // per query tile: one phase per accumulated P V half (O may be rescaled after it)
     uint64_t o_done[2];          // per query tile: last P V accumulated
+    uint64_t q_empty;            // the last Q K^T of the item has completed: the Q tiles may be overwritten (persistent grid)
+    uint64_t o_free[2];          // per query tile: the epilogue has read O out (128 arrivals): the next item may accumulate
     uint32_t tmem_base;
 };
 
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P_X aliases the first 64 columns of S_X
 // (bf16 pairs): the P chunk written after reading S chunk c only covers columns already consumed.
+//
+// PERSISTENT GRID (round 2): one CTA per SM walks the work items v = blockIdx.x, blockIdx.x + gridDim.x, ... (an item = what a CTA
+// of the round-1 grid did: one pair of query tiles, or one tile of a split pair).  TMEM allocation, barrier initialisation and
+// descriptor fetches happen once; every mbarrier keeps a running phase, and two barriers carry the cross-item dependencies:
+//   q_empty  -- the last Q K^T of an item has completed: the producer may overwrite the Q tiles with the next item's
+//   o_free[x]-- the softmax warpgroup has read O_x out: the MMA warp may start accumulating the next item into it
+// so the Q/K/V loads and the first score GEMM of item i+1 run while the warpgroups are still in the epilogue of item i (round 1
+// paid ~5 k cycles of prologue per CTA: 15 % of a 10-tile CTA at N = 1024, a third of a 4-tile CTA at N = 256).
 __global__ void __launch_bounds__(kAttn2Threads, 1)
 omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qt,
                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnParams p)
@@ -374,68 +392,9 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.a.L;
-    // Linear grid: CTA w < W0 = n_qpairs * Hq * B is the pair (b, h, qp) with the pair index fastest.  The last n_split of
-    // them would start in a final, mostly idle wave (one CTA per SM): each of those pairs is cut in two -- CTA w keeps
-    // tile A and the extra CTA w + n_split takes tile B -- so that the tail of the launch costs one tile, not two.
-    const int W0 = p.n_qpairs * p.a.Hq * p.a.B;
-    int w = (int)blockIdx.x;
-    int only = -1;                                          // -1: both tiles; 0: tile A only; 1: tile B only
-    if (w >= W0) { w -= p.n_split; only = 1; }
-    else if (w >= W0 - p.n_split) only = 0;
-    const int qp = p.n_qpairs - 1 - w % p.n_qpairs;         // heaviest (image-row) tiles first
-    const int h = (w / p.n_qpairs) % p.a.Hq, b = w / (p.n_qpairs * p.a.Hq);
-    const int G = p.a.Hq / p.a.Hkv;
-    const int hk = h / G;
-    // GQA-packed tail: when the last pair holds only R = Lq % 256 rows and R * G <= 128, the R rows of all G query heads
-    // of one KV head share ONE tile (row r of the tile = head h + r / R, sequence row r % R): they read the same K/V
-    // anyway.  With N + 2 = 1026 query rows per image this replaces 12 nearly empty tiles per image (11 % of all tiles)
-    // by 2.  The CTAs of the other G - 1 heads of the group have nothing to do.
-    const bool packed = p.tail_rows > 0 && qp == p.n_qpairs - 1;
-    if (packed && h % G != 0) return;
-    const int R = packed ? p.tail_rows : kBM;            // sequence rows covered by tile A
-    int P = p.a.pad_len[b], S = p.a.soi_idx[b];
-    P = max(0, min(P, L));
-    S = max(P, min(S, L));
-
-    // the two query tiles of this CTA (local rows lA/lB of q, absolute sequence rows iA/iB) and the kv tiles they need
-    const int Lq = p.a.Lq, q0 = p.a.q0;
-    const bool pair_has_b = !packed && qp * 2 * kBM + kBM < Lq;
-    if (!pair_has_b) {                                      // nothing to split
-        if (only == 1) return;
-        only = -1;
-    }
-    const int lA = qp * 2 * kBM + (only == 1 ? kBM : 0), lB = lA + kBM;
-    const int iA = q0 + lA, iB = q0 + lB;
-    const int iEnd = min(q0 + Lq, L);
-    const bool hasB = only < 0 && pair_has_b;
-    int tA0, tA1, tB0 = 0, tB1 = 0;
-    kv_range(iA, min(iA + R, iEnd), P, S, L, tA0, tA1);
-    if (hasB) kv_range(iB, min(iB + kBM, iEnd), P, S, L, tB0, tB1);
-    const int tU0 = hasB ? min(tA0, tB0) : tA0;
-    const int tU1 = hasB ? max(tA1, tB1) : tA1;
-    // union [jlo, jhi) of the allowed kv columns over the rows of each tile: a 64-column half outside it is skipped
-    const int jloA = (iA < P) ? 0 : P, jhiA = (min(iA + R, iEnd) > S) ? L : min(iA + R, iEnd);
-    const int jloB = (iB < P) ? 0 : P, jhiB = (min(iB + kBM, iEnd) > S) ? L : min(iB + kBM, iEnd);
-    auto half_on_slow = [&](int x, int t, int hf) -> bool {
-        const bool tile_on = x == 0 ? (t >= tA0 && t < tA1) : (hasB && t >= tB0 && t < tB1);
-        const int c0 = t * kBN + hf * 64 + kv_tile_offset(L, P);
-        return tile_on && c0 < (x == 0 ? jhiA : jhiB) && c0 + 64 > (x == 0 ? jloA : jloB);
-    };
-    // bit 2*(t - tU0) + hf of hmask[x]: half (t, hf) of tile x carries work (up to 32 kv tiles = L <= 4096)
-    unsigned long long hmask[2] = {0ull, 0ull};
-    for (int t = tU0; t < tU1; ++t)
-        for (int hf = 0; hf < 2; ++hf)
-            for (int x = 0; x < 2; ++x)
-                if (half_on_slow(x, t, hf)) hmask[x] |= 1ull << (2 * (t - tU0) + hf);
-    auto half_on = [&](int x, int t, int hf) -> bool { return (hmask[x] >> (2 * (t - tU0) + hf)) & 1ull; };
-
-    if (packed) {          // rows R*G .. 127 of the packed tile are not loaded: zero scores instead of stale shared memory
-        for (uint32_t o = (uint32_t)tid * 16u; o < kTileBytes; o += kAttn2Threads * 16u)
-            *reinterpret_cast<uint4*>(smem + kOff2QA + o) = make_uint4(0u, 0u, 0u, 0u);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
     if (tid == 0) {
         bar_init(&bars->q_full, 1);
+        bar_init(&bars->q_empty, 1);
         for (int s = 0; s < kKVStages; ++s) {
             bar_init(&bars->k_full[s], 1); bar_init(&bars->k_empty[s], 1);
             bar_init(&bars->v_full[s], 1); bar_init(&bars->v_empty[s], 1);
@@ -444,6 +403,7 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             for (int hf = 0; hf < 2; ++hf) { bar_init(&bars->s_full[x][hf], 1); bar_init(&bars->p_full[x][hf], 128); }
             bar_init(&bars->o_done[x], 1);
             bar_init(&bars->pv_done[x], 1);
+            bar_init(&bars->o_free[x], 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -452,20 +412,142 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp == 9 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_qt) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v) : "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    // test hook: cycle stamps of the heaviest CTA (blockIdx 0,0,0) at dbg[32768 + role*512 + iter*8 + event]
-    const bool tl = p.dbg && blockIdx.x == 0;
+    // test hook: cycle stamps of the first item of CTA 0 at dbg[32768 + role*512 + iter*8 + event]
+    bool tl = false;
     const uint32_t clk0 = (uint32_t)clock();
 #define UG_TL(role, iter, ev)                                                                            \
     do {                                                                                                 \
         if (tl && (iter) < 64) p.dbg[32768 + (role) * 512 + (iter) * 8 + (ev)] = (float)((uint32_t)clock() - clk0); \
     } while (0)
 
+    // running state of the roles across items (every thread walks the same item sequence)
+    int n_items = 0;                                  // items started by this CTA: phase of q_full / q_empty
+    int jj = 0;                                       // kv tiles of the items before this one: stage and phase of the K/V rings
+    int cnt_x[2] = {0, 0};                            // items in which query tile x carried work: phase of o_done / o_free
+    int np[2][2] = {{0, 0}, {0, 0}};                  // MMA warp: P halves consumed (phase of p_full)
+    int ns[2] = {0, 0};                               // softmax: halves (QK128: tiles, in ns[0]) processed (phase of s_full)
+    int n_pub = 0;                                    // softmax: P halves published so far by this warpgroup (phase of pv_done)
+
+    // Item list, heaviest first, walked round-robin by the CTAs (a static schedule: items of one class cost the same up to the
+    // pads of their sequence, so no dynamic ticket is needed):
+    //   [0, Wh - n_split)          pairs of query tiles (b, h, qp), qp fastest and descending (image rows first)
+    //   [.., + Wt)                 GQA-packed tail tiles (b, kv head): when the last pair holds only R = Lq % 256 rows and
+    //                              R * G <= 128, the R rows of all G query heads of one KV head share ONE tile (row r of the tile =
+    //                              head h + r / R, sequence row r % R): they read the same K/V anyway.  With N + 2 = 1026 query rows
+    //                              per image this replaces 12 nearly empty tiles per image (11 % of all tiles) by 2
+    //   [.., + n_split) x 2        the last n_split pairs, which would fall into a final, mostly idle round, cut in two: tile A only,
+    //                              then tile B only -- the tail of the launch costs one tile, not two
+    const int G = p.a.Hq / p.a.Hkv;
+    const int n_heavy = p.tail_rows > 0 ? p.n_qpairs - 1 : p.n_qpairs;      // non-packed pairs per (b, h)
+    const int Wh = n_heavy * p.a.Hq * p.a.B;
+    const int Wt = p.tail_rows > 0 ? p.a.Hkv * p.a.B : 0;
+    const int n_virtual = Wh + Wt + p.n_split;
+    const int Lq = p.a.Lq, q0 = p.a.q0;
+    const int iEnd = min(q0 + Lq, L);
+    // The items of this CTA are decoded ONCE, by one thread each, into a table in shared memory (up to kItemTable at a time) while
+    // the tensor memory is being allocated: between two items a role only reads a few words.  (Decoding per item in every warp
+    // -- divisions, kv ranges, masks, the pad_len / soi_idx loads -- kept the MMA warp off the tensor core for ~5 k cycles.)
+    auto decode_item = [&](int v, ItemInfo& it) {
+        int only = -1;                                      // -1: both tiles; 0: tile A only; 1: tile B only
+        bool packed = false;
+        int qp, h, b;
+        if (v >= Wh - p.n_split && v < Wh - p.n_split + Wt) {   // packed tail tile
+            const int u = v - (Wh - p.n_split);
+            packed = true;
+            qp = p.n_qpairs - 1;
+            h = (u % p.a.Hkv) * G;
+            b = u / p.a.Hkv;
+        } else {
+            int w = v;
+            if (v >= Wh + Wt) { w = v - Wt - p.n_split; only = 1; }
+            else if (v >= Wh - p.n_split + Wt) { w = v - Wt; only = 0; }
+            qp = n_heavy - 1 - w % n_heavy;
+            h = (w / n_heavy) % p.a.Hq;
+            b = w / (n_heavy * p.a.Hq);
+        }
+        const int R = packed ? p.tail_rows : kBM;        // sequence rows covered by tile A
+        int P = p.a.pad_len[b], S = p.a.soi_idx[b];
+        P = max(0, min(P, L));
+        S = max(P, min(S, L));
+        // the two query tiles of the item (local rows lA/lB of q, absolute sequence rows iA/iB) and the kv tiles they need
+        const bool pair_has_b = !packed && qp * 2 * kBM + kBM < Lq;
+        bool skip = false;
+        if (!pair_has_b) {                                  // nothing to split
+            if (only == 1) skip = true;
+            only = -1;
+        }
+        const int lA = qp * 2 * kBM + (only == 1 ? kBM : 0), lB = lA + kBM;
+        const int iA = q0 + lA, iB = q0 + lB;
+        const bool hasB = only < 0 && pair_has_b;
+        int tA0, tA1, tB0 = 0, tB1 = 0;
+        kv_range(iA, min(iA + R, iEnd), P, S, L, tA0, tA1);
+        if (hasB) kv_range(iB, min(iB + kBM, iEnd), P, S, L, tB0, tB1);
+        const int tU0 = hasB ? min(tA0, tB0) : tA0;
+        const int tU1 = hasB ? max(tA1, tB1) : tA1;
+        // union [jlo, jhi) of the allowed kv columns over the rows of each tile: a 64-column half outside it is skipped
+        const int jloA = (iA < P) ? 0 : P, jhiA = (min(iA + R, iEnd) > S) ? L : min(iA + R, iEnd);
+        const int jloB = (iB < P) ? 0 : P, jhiB = (min(iB + kBM, iEnd) > S) ? L : min(iB + kBM, iEnd);
+        const int kv_off = kv_tile_offset(L, P);
+        // bit 2*(t - tU0) + hf of hmask[x]: half (t, hf) of tile x carries work (up to 32 kv tiles = L <= 4096).  Half g = 2 t + hf
+        // covers the keys [64 g + kv_off, 64 g + kv_off + 64): it carries work iff it belongs to a kv tile of the query tile and
+        // meets the union [jlo, jhi) of the allowed keys of its rows -- a contiguous range of g: two shifts, not a loop
+        auto range_mask = [&](int t0x, int t1x, int jlo, int jhi) -> unsigned long long {
+            const int g_lo = max(2 * t0x, (jlo - kv_off) / 64), g_hi = min(2 * t1x, (jhi - kv_off + 63) / 64);
+            const int n = g_hi - g_lo;
+            if (n <= 0) return 0ull;
+            return (n >= 64 ? ~0ull : ((1ull << n) - 1ull)) << (g_lo - 2 * tU0);
+        };
+        it.hmask[0] = range_mask(tA0, tA1, jloA, jhiA);
+        it.hmask[1] = hasB ? range_mask(tB0, tB1, jloB, jhiB) : 0ull;
+        it.h = h; it.b = b; it.qp = qp; it.lA = lA; it.R = R; it.P = P; it.S = S;
+        it.tA0 = tA0; it.tA1 = tA1; it.tB0 = tB0; it.tB1 = tB1; it.tU0 = tU0; it.tU1 = tU1; it.kv_off = kv_off;
+        it.flags = (packed ? 1 : 0) | (hasB ? 2 : 0) | (skip ? 4 : 0);
+    };
+    ItemInfo* items = reinterpret_cast<ItemInfo*>(smem + kOff2Items);
+    const int n_mine = (int)blockIdx.x < n_virtual ? (n_virtual - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    for (int base = 0; base < n_mine; base += kItemTable) {
+    __syncthreads();                                    // base > 0: every role is done with the previous table
+    if (tid < kItemTable && base + tid < n_mine) decode_item((int)blockIdx.x + (base + tid) * (int)gridDim.x, items[tid]);
+    __syncthreads();
+    for (int ik = 0; ik < min(kItemTable, n_mine - base); ++ik) {
+    const ItemInfo& it = items[ik];
+    if (it.flags & 4) continue;
+    const bool packed = it.flags & 1, hasB = it.flags & 2;
+    const int h = it.h, b = it.b, qp = it.qp, lA = it.lA, lB = it.lA + kBM, R = it.R, P = it.P, S = it.S;
+    const int hk = h / G;
+    const int iA = q0 + lA, iB = q0 + lB;
+    const int tA0 = it.tA0, tA1 = it.tA1, tB0 = it.tB0, tB1 = it.tB1, tU0 = it.tU0, tU1 = it.tU1, kv_off = it.kv_off;
+    const unsigned long long hmask[2] = {it.hmask[0], it.hmask[1]};
+    auto half_on = [&](int x, int t, int hf) -> bool { return (hmask[x] >> (2 * (t - tU0) + hf)) & 1ull; };
+    tl = p.dbg && blockIdx.x == 0 && n_items == 0;
+    // item-boundary stamps of CTA 0 (test hook): dbg[32768 + 1536 + role * 128 + item * 8 + event], 16 items, 4 roles
+    const bool tli = p.dbg && blockIdx.x == 0 && n_items < 16;
+#define UG_TLI(role, ev)                                                                                             \
+    do {                                                                                                             \
+        if (tli) p.dbg[32768 + 1536 + (role) * 128 + n_items * 8 + (ev)] = (float)((uint32_t)clock() - clk0);        \
+    } while (0)
+
     if (warp == 8) {
         // =========================================================== TMA producer
+        if (lane == 0) UG_TLI(0, 0);
+        if (n_items > 0) bar_wait(&bars->q_empty, (uint32_t)(n_items - 1) & 1u);       // the previous item's last Q K^T is done
+        if (lane == 0) UG_TLI(0, 1);
+        if (packed) {      // rows R*G .. 127 of the packed tile are not loaded: zero scores instead of stale shared memory
+            for (uint32_t o = (uint32_t)lane * 16u; o < kTileBytes; o += 32u * 16u)
+                *reinterpret_cast<uint4*>(smem + kOff2QA + o) = make_uint4(0u, 0u, 0u, 0u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
         if (lane == 0) {
             if (packed) {      // box [64 d, R rows, G heads]: tile row g * R + r
                 bar_expect_tx(&bars->q_full, 2u * (uint32_t)(R * G) * 128u);
@@ -481,10 +563,10 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 tma_load_4d(smem + kOff2QB + kPanelBytes, &tm_q, &bars->q_full, 64, lB, h, b);
             }
             for (int t = tU0; t < tU1; ++t) {
-                const int j = t - tU0;
+                const int j = jj + t - tU0;
                 const int s = j % kKVStages;
                 const uint32_t ph = (uint32_t)(j / kKVStages) & 1u;
-                const int j0 = t * kBN + kv_tile_offset(L, P);          // may be negative for tile 0: those rows are zero-filled
+                const int j0 = t * kBN + kv_off;                       // may be negative for tile 0: those rows are zero-filled
                 bar_wait(&bars->k_empty[s], ph ^ 1u);
                 bar_expect_tx(&bars->k_full[s], kTileBytes);
                 tma_load_4d(smem + kOff2K + s * kTileBytes, &tm_k, &bars->k_full[s], 0, j0, hk, b);
@@ -494,9 +576,11 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 tma_load_4d(smem + kOff2V + s * kTileBytes, &tm_v, &bars->v_full[s], 0, j0, hk, b);
                 tma_load_4d(smem + kOff2V + s * kTileBytes + kPanelBytes, &tm_v, &bars->v_full[s], 64, j0, hk, b);
             }
+            UG_TLI(0, 2);
         }
+        __syncwarp();
     } else if (warp == 9) {
-        // =========================================================== MMA issuer (one thread)
+        // =========================================================== MMA issuer (one elected lane)
         // Each query tile is pipelined in two 64-column halves: while a warpgroup is in the softmax of one half the
         // tensor core computes the other half's P V and the next tile's Q K^T for the half just released, so the
         // softmax warps and the tensor core both stay busy.  Slot order per kv tile: (A,0) (B,0) (A,1) (B,1); in
@@ -505,14 +589,13 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             constexpr uint32_t idesc_qk = make_idesc(kBM, UG_ATTN_QK128 ? kBN : 64, 0, 0);      // S tile (or half): M=128, N=128 (64)
             constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);        // O:      M=128, N=128, K=64 per half
             const uint32_t qa_addr = s_u32(smem + kOff2QA), qb_addr = s_u32(smem + kOff2QB);
-            int np[2][2] = {{0, 0}, {0, 0}};                 // P halves consumed (phase of p_full)
             bool o_started[2] = {false, false};
             const uint32_t q_lo[2] = {desc_lo_kmajor(qa_addr), desc_lo_kmajor(qb_addr)};
             const uint32_t k_lo0 = desc_lo_kmajor(s_u32(smem + kOff2K)), v_lo0 = desc_lo_mnmajor(s_u32(smem + kOff2V));
             auto tile_on = [&](int x, int t) { return half_on(x, t, 0) || half_on(x, t, 1); };
             // scores of kv tile t for query tile x: the whole 128-column tile (hf < 0) or one 64-column half
             auto issue_qk = [&](int x, int t, int hf) {
-                const int j = t - tU0, s = j % kKVStages;
+                const int j = jj + t - tU0, s = j % kKVStages;
                 // K tile: two 64-wide d panels of [128 kv rows x 128 B]; kv rows 64*hf.. start 8 KB into each panel
                 const uint32_t kl = k_lo0 + (uint32_t)s * (kTileBytes >> 4) + (uint32_t)(hf > 0 ? 1 : 0) * ((64u * 128u) >> 4);
                 const uint32_t ql = q_lo[x];
@@ -526,7 +609,7 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 tc_commit(&bars->s_full[x][hf > 0 ? 1 : 0]);
             };
             auto wait_k = [&](int t) {
-                const int j = t - tU0, s = j % kKVStages;
+                const int j = jj + t - tU0, s = j % kKVStages;
                 bar_wait(&bars->k_full[s], (uint32_t)(j / kKVStages) & 1u);
                 tc_fence_after();
                 return s;
@@ -534,8 +617,10 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             auto last_pv = [&](int x, int t, int hf) {        // is (t, hf) the last half this tile accumulates?
                 return (hmask[x] >> (2 * (t - tU0) + hf + 1)) == 0ull;
             };
-            bar_wait(&bars->q_full, 0);
-            {   // prologue: scores of the first kv tile
+            if (lane == 0) UG_TLI(1, 0);
+            bar_wait(&bars->q_full, (uint32_t)n_items & 1u);
+            if (lane == 0) UG_TLI(1, 1);
+            {   // prologue: scores of the first kv tile (S_x is free: every P V of the previous item was issued before)
                 const int s = wait_k(tU0);
                 if (UG_ATTN_QK128) {
                     for (int x = 0; x < 2; ++x)
@@ -546,19 +631,24 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                             if (half_on(x, tU0, hf)) issue_qk(x, tU0, hf);
                 }
                 tc_commit(&bars->k_empty[s]);
+                if (tU0 + 1 >= tU1) tc_commit(&bars->q_empty);          // single kv tile: that was the last Q K^T of the item
+                if (lane == 0) UG_TLI(1, 2);
             }
             for (int t = tU0; t < tU1; ++t) {
-                const int j = t - tU0, s = j % kKVStages;
+                const int j = jj + t - tU0, s = j % kKVStages;
+                const int jl = t - tU0;
                 const bool next = t + 1 < tU1;
                 int sn = 0;
                 bool v_ready = false, k_ready = false;
                 for (int hf = 0; hf < 2; ++hf) {
                     for (int x = 0; x < 2; ++x) {
                         if (half_on(x, t, hf)) {
-                            if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 0);
+                            if (lane == 0) UG_TL(2, 4 * jl + 2 * hf + x, 0);
                             bar_wait(&bars->p_full[x][hf], (uint32_t)np[x][hf] & 1u);
-                            if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 1);
+                            if (lane == 0) UG_TL(2, 4 * jl + 2 * hf + x, 1);
                             if (!v_ready) { bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u); v_ready = true; }
+                            if (!o_started[x] && cnt_x[x] > 0)           // O_x still holds the previous item until its epilogue has read it
+                                bar_wait(&bars->o_free[x], (uint32_t)(cnt_x[x] - 1) & 1u);
                             tc_fence_after();
                             // V tile rows 64*hf.. (MN-major): 16 kv rows per MMA
                             const uint32_t vl = v_lo0 + (uint32_t)s * (kTileBytes >> 4) + (uint32_t)hf * ((64u * 128u) >> 4);
@@ -572,7 +662,7 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                             tc_commit(&bars->pv_done[x]);
                             o_started[x] = true;
                             ++np[x][hf];
-                            if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 2);
+                            if (lane == 0) UG_TL(2, 4 * jl + 2 * hf + x, 2);
                             if (last_pv(x, t, hf)) tc_commit(&bars->o_done[x]);
                         }
                         if (UG_ATTN_QK128) {
@@ -582,12 +672,12 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                             if (next && last_here && tile_on(x, t + 1)) {
                                 if (!k_ready) { sn = wait_k(t + 1); k_ready = true; }
                                 issue_qk(x, t + 1, -1);
-                                if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 3);
+                                if (lane == 0) UG_TL(2, 4 * jl + 2 * hf + x, 3);
                             }
                         } else if (next && half_on(x, t + 1, hf)) {
                             if (!k_ready) { sn = wait_k(t + 1); k_ready = true; }
                             issue_qk(x, t + 1, hf);
-                            if (lane == 0) UG_TL(2, 4 * j + 2 * hf + x, 3);
+                            if (lane == 0) UG_TL(2, 4 * jl + 2 * hf + x, 3);
                         }
                     }
                 }
@@ -596,8 +686,10 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 if (next) {
                     if (!k_ready) sn = wait_k(t + 1);
                     tc_commit(&bars->k_empty[sn]);
+                    if (t + 2 >= tU1) tc_commit(&bars->q_empty);        // the scores of the item's last kv tile are issued: Q may go
                 }
             }
+            if (lane == 0) UG_TLI(1, 3);
         }
     } else {
         // =========================================================== softmax / correction / epilogue, one warpgroup per query tile
@@ -628,9 +720,8 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             float l_run = 0.0f;
             const bool dump = p.dbg && x == 0 && qp == 0 && h == 0 && b == 0;
 
-            int ns[2] = {0, 0};                           // halves (QK128: tiles, in ns[0]) processed (phase of s_full)
-            int n_pub = 0;                                // P halves published so far by this warpgroup
-            bool o_live = false;                          // O_x holds (or is about to hold) an accumulation
+            bool o_live = false;                          // O_x holds (or is about to hold) an accumulation of THIS item
+            if (r == 0) UG_TLI(2 + x, 0);
             for (int t = t0; t < t1; ++t) {
               if (UG_ATTN_QK128 && (half_on(x, t, 0) || half_on(x, t, 1))) {      // the scores of the whole tile land at once
                   bar_wait(&bars->s_full[x][0], (uint32_t)ns[0] & 1u);
@@ -639,7 +730,7 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               for (int hf = 0; hf < 2; ++hf) {
                 if (!half_on(x, t, hf)) continue;
                 const int n = 2 * (t - t0) + hf;
-                const int j0 = t * kBN + hf * 64 + kv_tile_offset(L, P);
+                const int j0 = t * kBN + hf * 64 + kv_off;
                 const bool full_tile = (j0 >= max_lo) && (j0 + 64 <= min_hi);
                 const int clo = lo - j0, chi = hi - j0;
                 const uint32_t sh_addr = s_addr + (uint32_t)hf * 64u;
@@ -738,7 +829,9 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               }
             }
             // epilogue: O / l -> bf16 -> global
-            bar_wait(&bars->o_done[x], 0);
+            if (r == 0) UG_TLI(2 + x, 1);
+            bar_wait(&bars->o_done[x], (uint32_t)cnt_x[x] & 1u);
+            if (r == 0) UG_TLI(2 + x, 2);
             tc_fence_after();
             const float inv_l = 1.0f / l_run;
             __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.a.out) + (int64_t)b * p.a.o_sb + (int64_t)lrow * p.a.o_sl + (int64_t)ho * p.a.o_sh;
@@ -759,8 +852,17 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 }
             }
             tc_fence_before();
+            bar_arrive(&bars->o_free[x]);                // O_x has been read out: the next item may accumulate into it
+            if (r == 0) UG_TLI(2 + x, 3);
         }
     }
+    // every thread keeps the same books
+    jj += tU1 - tU0;
+    cnt_x[0] += 1;
+    cnt_x[1] += hasB ? 1 : 0;
+    ++n_items;
+    }       // items of the table
+    }       // tables
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
@@ -821,14 +923,14 @@ int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, c
     p.scale_log2 = a.scale * 1.4426950408889634f;
     p.n_qpairs = (a.Lq + 2 * kBM - 1) / (2 * kBM);
     p.tail_rows = tail_rows;
-    // CTAs that would start in a last, partly filled wave (one CTA per SM; a tail CTA counts as half a pair)
+    // pairs that would fall into a last, partly filled round (one CTA per SM; a packed tail tile counts as half a pair)
+    const int n_heavy = tail_rows ? p.n_qpairs - 1 : p.n_qpairs;
+    const int Wh = n_heavy * a.Hq * a.B, Wt = tail_rows ? a.Hkv * a.B : 0;
     {
-        const int n_full = a.Lq / (2 * kBM) * a.Hq * a.B;
-        const int n_tail = tail ? (tail_rows ? a.Hkv : a.Hq) * a.B : 0;
-        int k = num_sms > 0 ? (n_full + n_tail / 2) % num_sms : 0;
-        if (k > num_sms / 2 || k > n_full) k = 0;
+        int k = num_sms > 0 ? (Wh + Wt / 2) % num_sms : 0;
+        if (k > num_sms / 2 || k > Wh) k = 0;
         static const char* ov = getenv("UG_ATTN_NSPLIT");        // kernel experiments only (tools/bench_attention.py)
-        if (ov && atoi(ov) >= 0 && atoi(ov) <= n_full) k = atoi(ov);
+        if (ov && atoi(ov) >= 0 && atoi(ov) <= Wh) k = atoi(ov);
         p.n_split = k;
     }
     p.dbg = a.dbg;
@@ -840,7 +942,8 @@ int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, c
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    dim3 grid((unsigned)(p.n_qpairs * a.Hq * a.B + p.n_split));
+    const int n_virtual = Wh + Wt + p.n_split;
+    dim3 grid((unsigned)(num_sms > 0 && num_sms < n_virtual ? num_sms : n_virtual));      // persistent: one CTA per SM walks the items
     omni_attention_kernel<<<grid, kAttn2Threads, kAttn2Smem, stream>>>(tq, tqt, tk, tv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch: %s", cudaGetErrorString(e)); return (int)e; }

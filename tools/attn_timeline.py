@@ -26,3 +26,8 @@ for role in (0, 1):
 print("mma (tile A issuer) events per (kv tile, half): wait_start, p_full, pv_issued, qk_issued")
 for it in range(24):
     print(it // 2, it % 2, [int(x) for x in t[2, it, :4].tolist()])
+
+ti = dump[32768 + 1536:].cpu().view(4, 16, 8)
+print("item boundaries of CTA 0 (persistent grid): producer [start, q_empty ok, loads issued] | mma [start, q_full, first QK issued, done] | softmax A/B [start, wait o_done, o_done, o_free]")
+for it in range(8):
+    print(it, [int(x) for x in ti[0, it, :3].tolist()], [int(x) for x in ti[1, it, :4].tolist()], [int(x) for x in ti[2, it, :4].tolist()], [int(x) for x in ti[3, it, :4].tolist()])
