@@ -170,7 +170,8 @@ int ug_embed_rows(float* x, void* xb_bf16 /* nullable */, float* ss /* nullable 
  *                         the unfused autocast path holds) and w = Wg / Wu interleaved in blocks of 128 rows:
  *                         w[256 j + i] = Wg[128 j + i], w[256 j + 128 + i] = Wu[128 j + i], i < 128 (`pack_gate_up`
  *                         in ml_unigen_b200.ops does this once at load time); bias must be NULL
- * Supported: N % 256 == 0, K % 64 == 0, strides multiples of 8 elements, 16-byte aligned bases; fp32 accumulation.
+ * Supported: N % 256 == 0 (plain mode: N % 128 == 0), K % 64 == 0, strides multiples of 8 elements, 16-byte aligned bases; fp32
+ * accumulation.
  *
  * RMSNorm folding (row_ss != NULL; also ug_qkv_rope_bf16).  Qwen2RMSNorm (input_layernorm / post_attention_layernorm / norm)
  * commutes with the linear layer that follows it: (g * x / rms(x)) W^T = (1 / rms(x)) * (x (W diag g)^T).  The caller folds the
@@ -220,6 +221,26 @@ int ug_qkv_rope_bf16(const void* a, const void* w_qkv, const void* bias_qkv, voi
  *   ug_upsample2x_nhwc_bf16 : F.interpolate(scale_factor=2, mode="nearest") (common_modules.py:40), [B,H,W,C] -> [B,2H,2W,C]
  */
 int ug_lfq_unpack_bf16(const int64_t* ids, void* z_bf16, int64_t n, int dim, void* stream);
+
+/* Round 2: the convolutions and the attention block of the decoder on the library's own kernels (no cuDNN / SDPA call remains).
+ *   ug_lfq_postquant_bf16 : LFQ lookup + `post_quant_conv` (1x1, dim -> dim; magvitv2.py:217-230, 438-442) in one pass: the codebook
+ *                           entry is the +-1 bit vector of the id, so z[n, c] = bias[c] + sum_k w[c,k] * (+-1) (w fp32 [dim,dim],
+ *                           bias fp32 [dim] or NULL); rows of `cpad` >= dim channels, zero beyond dim (cpad = 64 feeds conv_in)
+ *   ug_conv_nhwc_bf16     : k x k convolution, stride 1, k = 3 with zero padding 1 (every `Conv2d(.., 3, 1, 1)` of VQGANDecoder,
+ *                           common_modules.py ResnetBlock / Upsample) or k = 1 (nin_shortcut, the q / k / v / proj_out of AttnBlock),
+ *                           as an IMPLICIT GEMM on the tcgen05 kernel of ug_gemm_bf16: x NHWC bf16 [B,H,W,Cin], y NHWC bf16
+ *                           [B,H,W,Cout]; w_packed bf16 [ceil128(Cout), k*k*ceil64(Cin)]: row o, column (ky*k + kx)*ceil64(Cin) + c
+ *                           = Conv2d.weight[o, c, ky, kx], zero in the padding (`pack_conv` in ml_unigen_b200.magvit); bias bf16
+ *                           [ceil128(Cout)] or NULL.  A rows = the pixels of [4 x 32] boxes fetched per (tap, 64-channel block) by
+ *                           4-D TMA with the tap's shift: image borders, partial boxes and channel padding are TMA out-of-bounds
+ *                           fill / clipping, so any H, W work; Cin % 8 == 0, Cout % 8 == 0.
+ *   ug_softmax_rows_bf16  : y = softmax(scale * x) per row of a bf16 matrix (AttnBlock, common_modules.py:171-215)
+ */
+int ug_lfq_postquant_bf16(const int64_t* ids, const float* w, const float* bias, void* z_bf16, int64_t n, int dim, int cpad, void* stream);
+int ug_conv_nhwc_bf16(const void* x_bf16, const void* w_packed_bf16, const void* bias_bf16, void* y_bf16,
+                      int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
+/* cols_valid <= cols: the row softmax is taken over the first cols_valid columns, the rest of the output row is zero (padded keys) */
+int ug_softmax_rows_bf16(const void* x_bf16, void* y_bf16, int64_t rows, int cols, int cols_valid, float scale, void* stream);
 size_t ug_groupnorm_workspace_floats(int B, int64_t HW, int C);
 int ug_groupnorm_nhwc_bf16(const void* x_bf16, const void* in_bias_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16,
                            float* workspace, int B, int64_t HW, int C, float eps, int swish, int stats_ready, void* stream);

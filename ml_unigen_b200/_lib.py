@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("UNIGEN_B200_LIB") or os.path.join(_HERE, "csrc", "lib
 UG_ABI_VERSION = 2
 SYMBOLS = (
     "ug_abi_version", "ug_last_error", "ug_decode_step_workspace_bytes", "ug_decode_step_bf16",
-    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_omni_attention_rows_bf16", "ug_add_rmsnorm", "ug_rope_qk", "ug_swiglu", "ug_embed_rows", "ug_gemm_bf16", "ug_gemm_residual_bf16", "ug_qkv_rope_bf16", "ug_lfq_unpack_bf16", "ug_groupnorm_workspace_floats", "ug_groupnorm_nhwc_bf16", "ug_bias_add_nhwc_bf16", "ug_bias_add_stats_nhwc_bf16", "ug_cfg_mix_bf16",
+    "ug_mask_by_random_topk", "ug_export_noise", "ug_omni_attention_bf16", "ug_omni_attention_rows_bf16", "ug_add_rmsnorm", "ug_rope_qk", "ug_swiglu", "ug_embed_rows", "ug_gemm_bf16", "ug_gemm_residual_bf16", "ug_qkv_rope_bf16", "ug_lfq_unpack_bf16", "ug_lfq_postquant_bf16", "ug_conv_nhwc_bf16", "ug_softmax_rows_bf16", "ug_groupnorm_workspace_floats", "ug_groupnorm_nhwc_bf16", "ug_bias_add_nhwc_bf16", "ug_bias_add_stats_nhwc_bf16", "ug_cfg_mix_bf16",
     "ug_upsample2x_nhwc_bf16",
 )
 
@@ -103,6 +103,12 @@ def lib() -> ctypes.CDLL:
                                    c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_float, c.c_void_p]
     L.ug_lfq_unpack_bf16.restype = c.c_int
     L.ug_lfq_unpack_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_void_p]
+    L.ug_lfq_postquant_bf16.restype = c.c_int
+    L.ug_lfq_postquant_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_int, c.c_void_p]
+    L.ug_conv_nhwc_bf16.restype = c.c_int
+    L.ug_conv_nhwc_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p]
+    L.ug_softmax_rows_bf16.restype = c.c_int
+    L.ug_softmax_rows_bf16.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_int, c.c_float, c.c_void_p]
     L.ug_groupnorm_workspace_floats.restype = c.c_size_t
     L.ug_groupnorm_workspace_floats.argtypes = [c.c_int, c.c_int64, c.c_int]
     L.ug_groupnorm_nhwc_bf16.restype = c.c_int

@@ -85,6 +85,13 @@ struct GemmParams {
     float* res_x;
     __nv_bfloat16* res_xb;
     float* res_ss;
+    // every unit is a 256 x 128 half tile (N % 256 == 128, e.g. the 128-channel layers of the pixel decoder): n_nhalf = N / 128
+    int all_half, n_nhalf;
+    // 3x3 convolution as an implicit GEMM (plain mode, conv_W > 0): A rows are the pixels of [4 rows x 32 columns] boxes of an NHWC
+    // activation [conv_B, conv_H, conv_W, Cin]; k block kb = tap * conv_cblk + channel block; the box of tap (ky, kx) is the
+    // output box shifted by (ky - 1, kx - 1), rows / columns outside the image zero-filled by TMA
+    int conv_B, conv_H, conv_W, conv_cblk, conv_boxes;
+    int conv_bpr, conv_bpi, conv_taps;       // boxes per row of boxes / per image (partial boxes are clipped by TMA), 9 or 1 taps
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,6 +163,19 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1)
 {
@@ -309,6 +329,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int n_units = p.n_rounds + ((p.split_tail ? cid < 2 * p.tail_tiles : cid < p.tail_tiles) ? 1 : 0);
     auto unit = [&](int i, int& mb, int& nb, int& half) {
         int tile;
+        if (p.all_half) {                       // tiles of 256 x 128: n index (in halves) fastest
+            tile = cid + i * ncl;
+            mb = tile / p.n_nhalf;
+            const int nh = tile - mb * p.n_nhalf;
+            nb = nh >> 1;
+            half = nh & 1;
+            return;
+        }
         if (i < p.n_rounds) {
             tile = cid + i * ncl;
             half = -1;
@@ -334,13 +362,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const int n0 = half < 0 ? nb * kGN + (int)rank * (kGN / 2) : nb * kGN + half * 128 + (int)rank * 64;
                 const CUtensorMap* wmap = half < 0 ? &tm_w : &tm_wh;
                 const uint32_t bytes = half < 0 ? 2 * kStageBytes : 2 * (kABytes + kBBytes / 2);
+                // convolution: this CTA's 128 rows are the pixels of box (cb, cy .. cy+3, cx .. cx+31)
+                int cb = 0, cy = 0, cx = 0;
+                if (p.conv_W) {
+                    const int box = mb * 2 + (int)rank, bpr = p.conv_bpr, bpi = p.conv_bpi;
+                    cb = box / bpi;
+                    const int r2 = box - cb * bpi;
+                    cy = (r2 / bpr) << 2;
+                    cx = (r2 % bpr) << 5;
+                }
+                int tap = 0, cblk = 0;
                 for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     bar_wait(&bars->empty[s], ph ^ 1u);
                     if (leader) bar_expect_tx(&bars->full[s], bytes);
                     const uint32_t fb = mapa(s_u32(&bars->full[s]), 0);
                     const uint32_t dst = s_u32(smem + s * kStageBytes);
-                    tma_load_2d_pair(dst, &tm_a, fb, kb * kGK, m0);
+                    if (p.conv_W) {
+                        const int ky = p.conv_taps == 1 ? 1 : tap / 3, kx = p.conv_taps == 1 ? 1 : tap - 3 * (tap / 3);
+                        tma_load_4d_pair(dst, &tm_a, fb, cblk * kGK, cx + kx - 1, cy + ky - 1, cb);
+                        if (++cblk == p.conv_cblk) { cblk = 0; ++tap; }
+                    } else {
+                        tma_load_2d_pair(dst, &tm_a, fb, kb * kGK, m0);
+                    }
                     tma_load_2d_pair(dst + kABytes, wmap, fb, kb * kGK, n0);
                 }
             }
@@ -662,7 +706,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     } else {
                         fence_async_smem();
                         epi_bar();
-                        if (issuer && m0 < p.M) {
+                        if (issuer && p.conv_W) {            // the rows of the staging tile are the pixels of one box of the output image
+                            const int box = mb * 2 + (int)rank;
+                            if (box < p.conv_boxes) {
+                                const int bpr = p.conv_bpr, bpi = p.conv_bpi;
+                                const int cb = box / bpi, r2 = box - cb * bpi, cy = (r2 / bpr) << 2, cx = (r2 % bpr) << 5;
+                                tma_store_4d(&tm_o, s_u32(stg), col0, cx, cy, cb);
+                                tma_store_4d(&tm_o, s_u32(stg) + 16384, col0 + 64, cx, cy, cb);
+                                bulk_commit();
+                            }
+                        } else if (issuer && m0 < p.M) {
                             tma_store_2d(&tm_o, s_u32(stg), col0, m0);
                             tma_store_2d(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
                             bulk_commit();
@@ -714,6 +767,20 @@ bool make_map_2d_f32(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// NHWC bf16 activation [B, H, W, C] (contiguous): boxes of [4 rows x 32 columns] pixels x 64 channels, 128-byte swizzle -- in
+// shared memory a box is a [128 pixels x 64 channels] K-major tile like any other A operand (and like the staging tile of the
+// epilogue, for the store)
+bool make_map_nhwc(EncodeTiledFn enc, CUtensorMap* m, const void* base, int B, int H, int W, int C)
+{
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, 32, 4, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool make_map_2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows = 128)
 {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -730,8 +797,17 @@ bool make_map_2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t ro
 int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* msg, size_t msg_len)
 {
     if (g.mode != kGemmPlain && g.mode != kGemmSwiGLU && g.mode != kGemmQkvRope && g.mode != kGemmResidual) { snprintf(msg, msg_len, "gemm: unsupported mode %d", g.mode); return -4; }
-    if (g.M < 1 || g.N < kGN || g.N % kGN || g.K < kGK || g.K % kGK) {
-        snprintf(msg, msg_len, "gemm: need N %% 256 == 0 and K %% 64 == 0 (M=%d N=%d K=%d)", g.M, g.N, g.K);
+    const bool all_half = g.N % kGN == 128;               // every unit is a 256 x 128 half tile
+    if (g.M < 1 || g.N < 128 || g.N % 128 || g.K < kGK || g.K % kGK || (all_half && g.mode != kGemmPlain)) {
+        snprintf(msg, msg_len, "gemm: need N %% 256 == 0 (plain mode: N %% 128 == 0) and K %% 64 == 0 (M=%d N=%d K=%d)", g.M, g.N, g.K);
+        return -4;
+    }
+    const bool conv = g.conv_W > 0;
+    const int conv_cblk = conv ? (g.conv_Cin + 63) / 64 : 0;
+    if (conv && (g.mode != kGemmPlain || g.conv_Cin % 8 || g.conv_Cout % 8 || (g.conv_taps != 9 && g.conv_taps != 1) ||
+                 g.K != g.conv_taps * conv_cblk * 64 || g.N < g.conv_Cout || g.conv_B < 1 || g.conv_H < 1)) {
+        snprintf(msg, msg_len, "conv: need Cin %% 8 == 0, Cout %% 8 == 0, taps 9 or 1, K = taps * ceil64(Cin), N = ceil128(Cout) (B=%d H=%d W=%d Cin=%d Cout=%d)",
+                 g.conv_B, g.conv_H, g.conv_W, g.conv_Cin, g.conv_Cout);
         return -4;
     }
     if (g.lda % 8 || g.ldw % 8 || (g.mode != kGemmResidual && g.ldo % 8)) { snprintf(msg, msg_len, "gemm: row strides must be multiples of 8 elements"); return -5; }
@@ -742,9 +818,10 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     const bool residual = g.mode == kGemmResidual;       // writes x / xb / ss with plain stores: no output tensor map
     if (residual && (!g.res_x || !g.res_xb || !g.res_ss)) { snprintf(msg, msg_len, "gemm: the residual mode needs x, xb and ss"); return -1; }
     if (g.row_ss && g.ss_parts < 1) { snprintf(msg, msg_len, "gemm: row_ss needs ss_parts >= 1"); return -4; }
-    if (!make_map_2d(enc, &ta, g.a, g.M, g.K, g.lda) || !make_map_2d(enc, &tw, g.w, g.N, g.K, g.ldw) ||
-        !make_map_2d(enc, &twh, g.w, g.N, g.K, g.ldw, 64) ||
-        !(residual ? make_map_2d_f32(enc, &to, g.res_x, g.M, g.N) : make_map_2d(enc, &to, g.out, g.M, n_out, g.ldo))) {
+    if (!(conv ? make_map_nhwc(enc, &ta, g.a, g.conv_B, g.conv_H, g.conv_W, g.conv_Cin) : make_map_2d(enc, &ta, g.a, g.M, g.K, g.lda)) ||
+        !make_map_2d(enc, &tw, g.w, g.N, g.K, g.ldw) || !make_map_2d(enc, &twh, g.w, g.N, g.K, g.ldw, 64) ||
+        !(residual ? make_map_2d_f32(enc, &to, g.res_x, g.M, g.N)
+                   : conv ? make_map_nhwc(enc, &to, g.out, g.conv_B, g.conv_H, g.conv_W, g.conv_Cout) : make_map_2d(enc, &to, g.out, g.M, n_out, g.ldo))) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled rejected the a/w/out layout");
         return -3;
     }
@@ -752,6 +829,14 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
     p.M = g.M; p.N = g.N; p.K = g.K;
     p.n_mblk = (g.M + 255) / 256;
     p.n_nblk = g.N / kGN;
+    p.all_half = all_half ? 1 : 0;
+    p.n_nhalf = g.N / 128;
+    p.conv_B = g.conv_B; p.conv_H = g.conv_H; p.conv_W = conv ? g.conv_W : 0; p.conv_cblk = conv_cblk;
+    p.conv_bpr = conv ? (g.conv_W + 31) / 32 : 0;
+    p.conv_bpi = conv ? p.conv_bpr * ((g.conv_H + 3) / 4) : 0;
+    p.conv_boxes = conv ? g.conv_B * p.conv_bpi : 0;
+    p.conv_taps = g.conv_taps;
+    if (conv) { p.n_mblk = (p.conv_boxes + 1) / 2; p.M = p.conv_boxes * 128; }
     p.n_kblk = g.K / kGK;
     p.mode = g.mode;
     p.bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
@@ -776,8 +861,8 @@ int launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, char* ms
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int max_clusters = num_sms / 2 > 0 ? num_sms / 2 : 1;
-    const int n_tiles = p.n_mblk * p.n_nblk;
-    const bool can_split = g.mode != kGemmSwiGLU;
+    const int n_tiles = all_half ? p.n_mblk * p.n_nhalf : p.n_mblk * p.n_nblk;
+    const bool can_split = g.mode != kGemmSwiGLU && !all_half;
     int n_clusters = max_clusters;
     if (n_tiles < max_clusters) n_clusters = can_split && 2 * n_tiles <= max_clusters ? 2 * n_tiles : n_tiles;
     p.n_rounds = n_tiles / n_clusters;

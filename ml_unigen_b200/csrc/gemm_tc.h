@@ -32,6 +32,12 @@ struct GemmArgs {
     const float* row_ss = nullptr;     // fp32 [M, ss_parts] or null
     int ss_parts = 0;
     float rms_eps = 0.0f;
+    // k x k convolution, k = 3 (zero padding 1) or 1, stride 1, as an implicit GEMM -- kGemmPlain only, conv_W > 0:
+    // a = NHWC bf16 activation [B,H,W,Cin] (contiguous), out = NHWC [B,H,W,Cout]; w = [N, K] with N = ceil128(Cout) rows (zero rows
+    // beyond Cout), K = taps * ceil64(Cin), k = tap * ceil64(Cin) + c (zero beyond Cin); bias (nullable) has N entries.
+    // A rows are the pixels of [4 x 32] boxes; partial boxes, image borders and the channel padding are TMA out-of-bounds
+    // zero fill (loads) / clipping (stores), so any H, W and any Cin, Cout that are multiples of 8 work.
+    int conv_B = 0, conv_H = 0, conv_W = 0, conv_Cin = 0, conv_Cout = 0, conv_taps = 9;
     // kGemmResidual only (contiguous rows of N elements)
     float* res_x = nullptr;
     void* res_xb = nullptr;

@@ -43,6 +43,71 @@ __global__ void __launch_bounds__(256) lfq_unpack_kernel(const int64_t* __restri
     }
 }
 
+// LFQ lookup + post_quant_conv in one pass (magvitv2.py:217-230 + the 1x1 `post_quant_conv` of :438-442): the codebook entry of a
+// token is the +-1 vector of its bits, so the 1x1 convolution is b[c] + sum_k W[c,k] * (+-1) -- no table, no GEMM.  The row is
+// written with `cpad` channels (>= dim, zero beyond dim): cpad = 64 feeds the implicit-GEMM conv_in without a padding pass.
+__global__ void __launch_bounds__(256) lfq_postquant_kernel(const int64_t* __restrict__ ids, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ z, int64_t n,
+                                                            int dim, int cpad)
+{
+    const int64_t total = n * cpad;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = idx / cpad;
+        const int c = (int)(idx - t * cpad);
+        float acc = 0.0f;
+        if (c < dim) {
+            const int64_t id = ids[t];
+            acc = bias ? bias[c] : 0.0f;
+            for (int k = 0; k < dim; ++k) {
+                const float wk = w[c * dim + k];
+                acc += ((id >> (dim - 1 - k)) & 1) ? wk : -wk;
+            }
+        }
+        z[idx] = __float2bfloat16(acc);
+    }
+}
+
+// row softmax of a bf16 matrix (the single attention block of the decoder: 1024 x 1024 scores per image): one warp per row,
+// y = softmax(scale * x) in fp32, bf16 out; cols % 8 == 0
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t rows, int vecs_all,
+                                                           int vecs, float scale_log2)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const uint4* xr = x + row * vecs_all;
+    float mx = -INFINITY;
+    for (int v = lane; v < vecs; v += 32) {
+        const uint4 u = xr[v];
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(bf_lo(u.x), bf_hi(u.x)), fmaxf(bf_lo(u.y), bf_hi(u.y))),
+                             fmaxf(fmaxf(bf_lo(u.z), bf_hi(u.z)), fmaxf(bf_lo(u.w), bf_hi(u.w)))));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    const float m2 = mx * scale_log2;
+    float sum = 0.0f;
+    for (int v = lane; v < vecs; v += 32) {
+        const uint4 u = xr[v];
+        sum += exp2f(bf_lo(u.x) * scale_log2 - m2) + exp2f(bf_hi(u.x) * scale_log2 - m2) + exp2f(bf_lo(u.y) * scale_log2 - m2) +
+               exp2f(bf_hi(u.y) * scale_log2 - m2) + exp2f(bf_lo(u.z) * scale_log2 - m2) + exp2f(bf_hi(u.z) * scale_log2 - m2) +
+               exp2f(bf_lo(u.w) * scale_log2 - m2) + exp2f(bf_hi(u.w) * scale_log2 - m2);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float inv = 1.0f / sum;
+    uint4* yr = y + row * vecs_all;
+    for (int v = vecs + lane; v < vecs_all; v += 32) yr[v] = make_uint4(0u, 0u, 0u, 0u);      // padded keys
+    for (int v = lane; v < vecs; v += 32) {
+        const uint4 u = xr[v];
+        uint4 o;
+        o.x = pack2(exp2f(bf_lo(u.x) * scale_log2 - m2) * inv, exp2f(bf_hi(u.x) * scale_log2 - m2) * inv);
+        o.y = pack2(exp2f(bf_lo(u.y) * scale_log2 - m2) * inv, exp2f(bf_hi(u.y) * scale_log2 - m2) * inv);
+        o.z = pack2(exp2f(bf_lo(u.z) * scale_log2 - m2) * inv, exp2f(bf_hi(u.z) * scale_log2 - m2) * inv);
+        o.w = pack2(exp2f(bf_lo(u.w) * scale_log2 - m2) * inv, exp2f(bf_hi(u.w) * scale_log2 - m2) * inv);
+        yr[v] = o;
+    }
+}
+
 // grid (chunks, B); block kGnThreads.  Thread t owns vector slot t % (C/8) (8 consecutive channels) of the rows
 // t / (C/8) + k * (kGnThreads / (C/8)) of its chunk.  Requires C % 8 == 0 and kGnThreads % (C/8) == 0.
 // kFused: the pass also PRODUCES the tensor the statistics are taken of: out = x + in_bias (+ r (+ bias_r)) is rounded to bf16,
@@ -218,6 +283,22 @@ cudaError_t launch_lfq_unpack(const int64_t* ids, void* z, int64_t n, int dim, c
 {
     if (n < 1 || dim < 1 || dim > 62) return cudaErrorInvalidValue;
     lfq_unpack_kernel<<<grid_for(n * dim, 256), 256, 0, stream>>>(ids, reinterpret_cast<__nv_bfloat16*>(z), n, dim);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lfq_postquant(const int64_t* ids, const float* w, const float* bias, void* z, int64_t n, int dim, int cpad,
+                                 cudaStream_t stream)
+{
+    if (n < 1 || dim < 1 || dim > 62 || cpad < dim) return cudaErrorInvalidValue;
+    lfq_postquant_kernel<<<grid_for(n * cpad, 256), 256, 0, stream>>>(ids, w, bias, reinterpret_cast<__nv_bfloat16*>(z), n, dim, cpad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_softmax_rows(const void* x, void* y, int64_t rows, int cols, int cols_valid, float scale, cudaStream_t stream)
+{
+    if (rows < 1 || cols < 8 || cols % 8 || cols_valid < 8 || cols_valid % 8 || cols_valid > cols) return cudaErrorInvalidValue;
+    softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), rows,
+                                                                       cols / 8, cols_valid / 8, scale * 1.4426950408889634f);
     return cudaGetLastError();
 }
 

@@ -9,6 +9,15 @@ namespace ugk {
 // ids int64 [n] -> z bf16 [n, dim] (= NHWC [B,h,w,dim]): +-1, channel c = bit (dim-1-c) of the index
 cudaError_t launch_lfq_unpack(const int64_t* ids, void* z_bf16, int64_t n, int dim, cudaStream_t stream);
 
+// LFQ lookup + post_quant_conv (1x1, dim -> dim, w fp32 [dim, dim], bias fp32 [dim] or null) in one pass; z bf16 [n, cpad], channels
+// >= dim zero
+cudaError_t launch_lfq_postquant(const int64_t* ids, const float* w, const float* bias, void* z_bf16, int64_t n, int dim, int cpad,
+                                 cudaStream_t stream);
+
+// y = softmax(scale * x) per row over the first cols_valid columns (the others: zero), bf16 [rows, cols] in and out (fp32 inside);
+// cols % 8 == 0, cols_valid % 8 == 0
+cudaError_t launch_softmax_rows(const void* x_bf16, void* y_bf16, int64_t rows, int cols, int cols_valid, float scale, cudaStream_t stream);
+
 // GroupNorm(32 groups, eps) (+ swish) over x bf16 NHWC [B, HW, C]; partial: fp32 [B, chunks, 32, 2] scratch, stats: fp32 [B, 32, 2]
 size_t groupnorm_workspace_floats(int B, int64_t HW, int C);
 // in_bias (nullable, bf16 [C]) is added to x first: the bias of the convolution that produced x

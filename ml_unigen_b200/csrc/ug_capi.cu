@@ -347,8 +347,8 @@ extern "C" int ug_gemm_bf16(const void* a, const void* w, const void* bias, void
     if (!a || !w || !out) return fail(UG_ERR_NULL, "ug_gemm_bf16: null pointer");
     if (mode != UG_GEMM_PLAIN && mode != UG_GEMM_SWIGLU) return fail(UG_ERR_SHAPE, "ug_gemm_bf16: unknown mode %d", mode);
     if (mode == UG_GEMM_SWIGLU && bias) return fail(UG_ERR_SHAPE, "ug_gemm_bf16: the SwiGLU mode takes no bias");
-    if (M < 1 || N < 256 || N % 256 || K < 64 || K % 64)
-        return fail(UG_ERR_SHAPE, "ug_gemm_bf16: need M >= 1, N %% 256 == 0, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+    if (M < 1 || N < 128 || N % 128 || (N % 256 && mode != UG_GEMM_PLAIN) || K < 64 || K % 64)
+        return fail(UG_ERR_SHAPE, "ug_gemm_bf16: need M >= 1, N %% 256 == 0 (plain mode: N %% 128 == 0), K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
     const int n_out = mode == UG_GEMM_SWIGLU ? N / 2 : N;
     if (lda < K || ldw < K || ldo < n_out || lda % 8 || ldw % 8 || ldo % 8)
         return fail(UG_ERR_SHAPE, "ug_gemm_bf16: row strides must cover the row and be multiples of 8 elements");
@@ -432,6 +432,54 @@ extern "C" int ug_lfq_unpack_bf16(const int64_t* ids, void* z_bf16, int64_t n, i
     if (n < 1 || dim < 1 || dim > 62) return fail(UG_ERR_SHAPE, "ug_lfq_unpack_bf16: bad shape");
     cudaError_t e = ugk::launch_lfq_unpack(ids, z_bf16, n, dim, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "ug_lfq_unpack_bf16 launch");
+    return UG_OK;
+}
+
+extern "C" int ug_lfq_postquant_bf16(const int64_t* ids, const float* w, const float* bias, void* z_bf16, int64_t n, int dim, int cpad,
+                                     void* stream)
+{
+    if (!ids || !w || !z_bf16) return fail(UG_ERR_NULL, "ug_lfq_postquant_bf16: null pointer");
+    if (n < 1 || dim < 1 || dim > 62 || cpad < dim) return fail(UG_ERR_SHAPE, "ug_lfq_postquant_bf16: bad shape");
+    cudaError_t e = ugk::launch_lfq_postquant(ids, w, bias, z_bf16, n, dim, cpad, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_lfq_postquant_bf16 launch");
+    return UG_OK;
+}
+
+extern "C" int ug_softmax_rows_bf16(const void* x_bf16, void* y_bf16, int64_t rows, int cols, int cols_valid, float scale, void* stream)
+{
+    if (!x_bf16 || !y_bf16) return fail(UG_ERR_NULL, "ug_softmax_rows_bf16: null pointer");
+    if (rows < 1 || cols < 8 || cols % 8 || cols_valid < 8 || cols_valid % 8 || cols_valid > cols)
+        return fail(UG_ERR_SHAPE, "ug_softmax_rows_bf16: need cols %% 8 == 0 and 8 <= cols_valid <= cols, cols_valid %% 8 == 0");
+    if (!aligned16(x_bf16) || !aligned16(y_bf16)) return fail(UG_ERR_ALIGN, "ug_softmax_rows_bf16: pointers must be 16-byte aligned");
+    cudaError_t e = ugk::launch_softmax_rows(x_bf16, y_bf16, rows, cols, cols_valid, scale, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ug_softmax_rows_bf16 launch");
+    return UG_OK;
+}
+
+extern "C" int ug_conv_nhwc_bf16(const void* x_bf16, const void* w_packed_bf16, const void* bias_bf16, void* y_bf16,
+                                 int B, int H, int W, int Cin, int Cout, int ksize, void* stream)
+{
+    if (!x_bf16 || !w_packed_bf16 || !y_bf16) return fail(UG_ERR_NULL, "ug_conv_nhwc_bf16: null pointer");
+    if (B < 1 || H < 1 || W < 1 || Cin < 8 || Cin % 8 || Cout < 8 || Cout % 8 || (ksize != 3 && ksize != 1))
+        return fail(UG_ERR_SHAPE, "ug_conv_nhwc_bf16: need Cin %% 8 == 0, Cout %% 8 == 0, ksize 3 or 1 (B=%d H=%d W=%d Cin=%d Cout=%d k=%d)",
+                    B, H, W, Cin, Cout, ksize);
+    const long long boxes = (long long)B * ((H + 3) / 4) * ((W + 31) / 32);
+    if (boxes * 128 >= (1ll << 31)) return fail(UG_ERR_SHAPE, "ug_conv_nhwc_bf16: too many pixels");
+    if (!aligned16(x_bf16) || !aligned16(w_packed_bf16) || !aligned16(y_bf16) || (bias_bf16 && !aligned16(bias_bf16)))
+        return fail(UG_ERR_ALIGN, "ug_conv_nhwc_bf16: pointers must be 16-byte aligned");
+    int major = 0;
+    const int sms = sm_count(&major);
+    if (major != 10) return fail(UG_ERR_DEVICE, "ug_conv_nhwc_bf16 needs an sm_100 device (tcgen05), found compute capability %d.x", major);
+    const int taps = ksize * ksize, cin_pad = (Cin + 63) / 64 * 64, n_pad = (Cout + 127) / 128 * 128;
+    ugk::GemmArgs g;
+    g.a = x_bf16; g.w = w_packed_bf16; g.bias = bias_bf16; g.out = y_bf16;
+    g.M = (int)(boxes * 128); g.N = n_pad; g.K = taps * cin_pad;
+    g.lda = Cin; g.ldw = g.K; g.ldo = Cout;
+    g.mode = ugk::kGemmPlain;
+    g.conv_B = B; g.conv_H = H; g.conv_W = W; g.conv_Cin = Cin; g.conv_Cout = Cout; g.conv_taps = taps;
+    char msg[256] = "";
+    const int rc = ugk::launch_gemm_tc(g, sms, static_cast<cudaStream_t>(stream), msg, sizeof msg);
+    if (rc != 0) return fail(rc, "ug_conv_nhwc_bf16: %s", msg);
     return UG_OK;
 }
 

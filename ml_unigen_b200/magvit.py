@@ -3,19 +3,19 @@
 `LFQuantizer.get_codebook_entry` :217-230 + `VQGANDecoder.forward` :371-408; blocks in common_modules.py:19-43,
 171-215, 301-360), as the callers run it right after `t2i_generate` (evaluation/inference_geneval.py:266-267).
 
-Layout for one B200: activations NHWC bf16 (`channels_last`), so that every convolution is a cuDNN implicit GEMM on
-tensor cores without layout changes, and everything between the convolutions is one hand-written, single-purpose pass
-over HBM (csrc/magvit_ops.cu): the LFQ bit unpack (no embedding table), GroupNorm(32)+swish in one statistics pass and one
-apply pass (the reference: group_norm, sigmoid, mul = 5 passes), nearest-2x upsampling.  The convolutions and the single
-mid-block attention (1024 tokens, one head of 512 channels: outside the D=128 omni-attention kernel) are library calls
-(cuDNN / torch SDPA), like the plain cuBLAS GEMMs of the backbone.  Weights: the reference's `VQGANDecoder` state dict.
-There is no CPU path."""
+Layout for one B200: activations NHWC bf16, every convolution an IMPLICIT GEMM on the library's own tcgen05 kernel
+(`ug_conv_nhwc_bf16`: the A operand of tap (ky, kx) is the output's [4 x 32]-pixel box shifted by the tap, fetched by 4-D TMA;
+borders, partial boxes and channel padding are TMA out-of-bounds fill), the single attention block of the decoder (1024 tokens,
+one head of 512 channels) two plain GEMMs of the same kernel around a row-softmax kernel, and everything between the
+convolutions one hand-written, single-purpose pass over HBM (csrc/magvit_ops.cu): LFQ lookup + post_quant_conv (no embedding
+table, no GEMM), GroupNorm(32)+swish in one statistics pass and one apply pass (the reference: group_norm, sigmoid, mul = 5
+passes), bias + residual adds, nearest-2x upsampling.  No cuDNN / cuBLAS / SDPA call remains (round 1 ran the convolutions on
+cuDNN and the attention on torch SDPA).  Weights: the reference's `VQGANDecoder` state dict.  There is no CPU path."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib, ops
 
@@ -104,12 +104,72 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def _conv(x_nhwc: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], padding: int) -> torch.Tensor:
-    """cuDNN convolution on an NHWC bf16 activation; returns NHWC (contiguous).  The big convolutions are called with
-    b = None: torch adds a convolution bias in a separate, non-vectorised broadcast kernel (326 us per convolution at
-    16 x 512 x 512 x 128 -- a third of the decoder before it was folded into the consuming kernels)."""
-    y = F.conv2d(x_nhwc.permute(0, 3, 1, 2), w, b, padding=padding)        # NCHW view of channels_last memory
-    return y.permute(0, 2, 3, 1).contiguous()                                # no copy when cuDNN kept channels_last
+def _ceil(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, cin_pad_to: Optional[int] = None):
+    """Conv2d weight [Cout, Cin, k, k] (k = 3 or 1) -> the layout `ug_conv_nhwc_bf16` reads: bf16 [ceil128(Cout), k*k*ceil64(Cin')]
+    with column (ky*k + kx)*ceil64(Cin') + c, zero in the padding (Cin' = cin_pad_to when the activation carries zero channels
+    beyond Cin, e.g. the 64-channel output of `lfq_postquant`); bias -> bf16 [ceil128(Cout)] (or None)."""
+    Cout, Cin, k, _ = weight.shape
+    cin = cin_pad_to or Cin
+    cp, npad = _ceil(cin, 64), _ceil(Cout, 128)
+    w = torch.zeros(npad, k * k, cp, dtype=torch.bfloat16, device=weight.device)
+    w[:Cout, :, :Cin] = weight.detach().permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).to(torch.bfloat16)
+    b = None
+    if bias is not None:
+        b = torch.zeros(npad, dtype=torch.bfloat16, device=weight.device)
+        b[:Cout] = bias.detach().to(torch.bfloat16)
+    return w.reshape(npad, k * k * cp).contiguous(), b
+
+
+def conv_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ksize: int) -> torch.Tensor:
+    """k x k convolution (k = 3: zero padding 1; k = 1), stride 1, on an NHWC bf16 activation [B,H,W,Cin] -> [B,H,W,cout], one
+    launch of the tcgen05 implicit-GEMM kernel; `w_packed`, `bias` from `pack_conv`."""
+    ops._need_cuda(x, w_packed, bias)
+    B, H, W, Cin = x.shape
+    if x.dtype != torch.bfloat16 or not x.is_contiguous() or w_packed.dtype != torch.bfloat16 or not w_packed.is_contiguous():
+        raise ValueError("x must be contiguous bf16 NHWC, w_packed contiguous bf16")
+    if tuple(w_packed.shape) != (_ceil(cout, 128), ksize * ksize * _ceil(Cin, 64)):
+        raise ValueError(f"w_packed must be [{_ceil(cout, 128)}, {ksize * ksize * _ceil(Cin, 64)}] for Cin={Cin}, cout={cout}, k={ksize}")
+    y = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().ug_conv_nhwc_bf16(ops._ptr(x), ops._ptr(w_packed), ops._ptr(bias), ops._ptr(y), B, H, W, Cin, cout, ksize,
+                                            ops._stream()))
+    return y
+
+
+def lfq_postquant(ids: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], dim: int = 13, cpad: int = 64) -> torch.Tensor:
+    """int64 [B,N] -> bf16 NHWC [B,h,w,cpad]: LFQ codebook entry (+-1 bits) through the 1x1 `post_quant_conv` (w fp32 [dim,dim], b fp32
+    [dim] or None) in one pass; channels >= dim are zero."""
+    ops._need_cuda(ids, w, b)
+    B, N = ids.shape
+    h = int(round(N ** 0.5))
+    if h * h != N or ids.dtype != torch.int64 or w.dtype != torch.float32 or tuple(w.shape) != (dim, dim) or not w.is_contiguous():
+        raise ValueError("ids must be int64 [B, N] with N a square, w contiguous fp32 [dim, dim]")
+    z = torch.empty(B, h, h, cpad, dtype=torch.bfloat16, device=ids.device)
+    _lib.check(_lib.lib().ug_lfq_postquant_bf16(ops._ptr(ids.contiguous()), ops._ptr(w), ops._ptr(b), ops._ptr(z), B * N, dim, cpad, ops._stream()))
+    return z
+
+
+def softmax_rows(x: torch.Tensor, scale: float, cols_valid: Optional[int] = None) -> torch.Tensor:
+    """bf16 [R, C] -> softmax(scale * x[:, :cols_valid]) per row (columns beyond cols_valid: zero), bf16."""
+    ops._need_cuda(x)
+    R, C = x.shape
+    if x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise ValueError("x must be contiguous bf16 [R, C]")
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().ug_softmax_rows_bf16(ops._ptr(x), ops._ptr(y), R, C, C if cols_valid is None else cols_valid, float(scale), ops._stream()))
+    return y
+
+
+def _pad2d(t: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """zero-pad a 2-D tensor to [rows, cols] (a no-op view at the default architecture's shapes)."""
+    if t.shape[0] == rows and t.shape[1] == cols and t.is_contiguous():
+        return t
+    out = torch.zeros(rows, cols, dtype=t.dtype, device=t.device)
+    out[: t.shape[0], : t.shape[1]] = t
+    return out
 
 
 class MagvitV2DecoderB200:
@@ -125,12 +185,39 @@ class MagvitV2DecoderB200:
         self.device = torch.device(device)
         self.num_res_blocks = list(num_res_blocks)
         self.codebook_dim = codebook_dim
-        self.w: Dict[str, torch.Tensor] = {}
-        for k, v in weights.items():
-            t = v.detach().to(self.device, torch.bfloat16)
-            if t.dim() == 4:
-                t = t.contiguous(memory_format=torch.channels_last)
-            self.w[k] = t.contiguous() if t.dim() != 4 else t
+        self.w: Dict[str, torch.Tensor] = {}          # norm gains / biases and conv biases, bf16
+        self.cw: Dict[str, tuple] = {}                # conv name -> (packed weight, packed bias, Cout, ksize)
+        # the parameters as the kernels see them (rounded to bf16), in fp32: what the fp32 oracle of the tests is run with
+        self.raw = {k: v.detach().to(self.device, torch.bfloat16).float() for k, v in weights.items()}
+        convs = {k[: -len(".weight")] for k, v in weights.items() if v.dim() == 4}
+        for k, t in self.raw.items():
+            name = k.rsplit(".", 1)[0]
+            if name not in convs:                         # GroupNorm gain / bias
+                self.w[k] = t.to(torch.bfloat16).contiguous()
+            elif k.endswith(".bias"):
+                self.w[k] = t.to(torch.bfloat16).contiguous()
+            elif name == "post_quant_conv":               # fused with the LFQ lookup (fp32 matrix, lfq_postquant)
+                self.pq_w = t.reshape(t.shape[0], t.shape[1]).contiguous()
+                self.pq_b = self.raw.get(name + ".bias")
+            else:
+                cin_pad = 64 if name == "conv_in" else None   # its input is the 64-channel (zero-padded) output of lfq_postquant
+                wp, bp = pack_conv(t, self.raw.get(name + ".bias"), cin_pad_to=cin_pad)
+                self.cw[name] = (wp, bp, t.shape[0], t.shape[2])
+        # AttnBlock: softmax rows sum to one, so P (V + 1 b_v^T) = P V + b_v: the value bias moves behind the attention and is
+        # folded into proj_out's bias (b_p + W_p b_v) once here; the v projection itself then needs no bias
+        if "mid.attn_1.proj_out" in self.cw:
+            wp32 = self.raw["mid.attn_1.proj_out.weight"].reshape(self.raw["mid.attn_1.proj_out.weight"].shape[0], -1)
+            b_eff = self.raw["mid.attn_1.proj_out.bias"] + wp32 @ self.raw["mid.attn_1.v.bias"]
+            wpk, _, co, ks = self.cw["mid.attn_1.proj_out"]
+            bpad = torch.zeros(wpk.shape[0], dtype=torch.bfloat16, device=self.device)
+            bpad[:co] = b_eff.to(torch.bfloat16)
+            self.cw["mid.attn_1.proj_out"] = (wpk, bpad, co, ks)
+
+    def _conv(self, name: str, x: torch.Tensor, with_bias: bool) -> torch.Tensor:
+        wp, bp, cout, ks = self.cw[name]
+        c8 = _ceil(cout, 8)                               # TMA needs 16-byte row strides: conv_out's 3 channels are stored as 8
+        y = conv_nhwc(x, wp, bp if with_bias else None, c8, ks)
+        return y if c8 == cout else y[..., :cout]
 
     @classmethod
     def random_init(cls, device, seed: int = 0, ch: int = 128, ch_mult: Sequence[int] = (1, 1, 2, 2, 4),
@@ -176,28 +263,37 @@ class MagvitV2DecoderB200:
 
     # ---------------------------------------------------------------------------------------------
     def _res(self, p: str, x: torch.Tensor, x_stats_ready: bool = False, emit_stats: bool = False) -> torch.Tensor:
-        """ResnetBlock.  `x_stats_ready`: x comes from a block that ran with `emit_stats` (its residual add already summed
+        """ResnetBlock (`p` ends with a dot).  `x_stats_ready`: x comes from a block that ran with `emit_stats` (its residual add already summed
         x for this block's norm1); `emit_stats`: the next consumer of the result is a GroupNorm over the same tensor."""
         w = self.w
         h = groupnorm_swish(x, w[p + "norm1.weight"], w[p + "norm1.bias"], stats_ready=x_stats_ready)
-        h = _conv(h, w[p + "conv1.weight"], None, 1)
-        h = groupnorm_swish(h, w[p + "norm2.weight"], w[p + "norm2.bias"], out=h, in_bias=w[p + "conv1.bias"])
-        h = _conv(h, w[p + "conv2.weight"], None, 1)
-        if p + "nin_shortcut.weight" in w:
-            xs = _conv(x, w[p + "nin_shortcut.weight"], None, 0)
+        h = self._conv(p + "conv1", h, with_bias=True)               # the bias rides in the GEMM epilogue
+        h = groupnorm_swish(h, w[p + "norm2.weight"], w[p + "norm2.bias"], out=h)
+        h = self._conv(p + "conv2", h, with_bias=False)              # its bias joins the residual add below (one pass, + GroupNorm sums)
+        if p + "nin_shortcut" in self.cw:
+            xs = self._conv(p + "nin_shortcut", x, with_bias=False)
             return bias_add(h, w[p + "conv2.bias"], xs, w[p + "nin_shortcut.bias"], emit_stats=emit_stats)
         return bias_add(h, w[p + "conv2.bias"], x, emit_stats=emit_stats)
 
     def _attn(self, p: str, x: torch.Tensor) -> torch.Tensor:
+        """AttnBlock (common_modules.py:171-215): GroupNorm, 1x1 q/k/v, softmax(q k^T / sqrt(C)) v, 1x1 proj_out, residual.  One head of
+        C channels over H*W tokens: per image two plain tcgen05 GEMMs (scores, P V) around the row-softmax kernel."""
         w = self.w
         B, H, W, C = x.shape
-        h = groupnorm_swish(x, w[p + "norm.weight"], w[p + "norm.bias"], swish=False).view(B, H * W, C)
-        q = F.linear(h, w[p + "q.weight"].view(C, C), w[p + "q.bias"])
-        k = F.linear(h, w[p + "k.weight"].view(C, C), w[p + "k.bias"])
-        v = F.linear(h, w[p + "v.weight"].view(C, C), w[p + "v.bias"])
-        o = F.scaled_dot_product_attention(q.unsqueeze(1), k.unsqueeze(1), v.unsqueeze(1), scale=float(C) ** -0.5).squeeze(1)
-        o = F.linear(o, w[p + "proj_out.weight"].view(C, C), w[p + "proj_out.bias"])
-        return x + o.view(B, H, W, C)
+        T = H * W
+        h = groupnorm_swish(x, w[p + "norm.weight"], w[p + "norm.bias"], swish=False)
+        q = self._conv(p + "q", h, with_bias=True).view(B, T, C)
+        k = self._conv(p + "k", h, with_bias=True).view(B, T, C)
+        v = self._conv(p + "v", h, with_bias=False).view(B, T, C)          # b_v is folded into proj_out's bias (see __init__)
+        Tp, Cp, Cn = _ceil(T, 128), _ceil(C, 64), _ceil(C, 128)            # GEMM shape limits: N % 128, K % 64 (no-ops at C=512, T=1024)
+        o = torch.empty(B, T, C, dtype=torch.bfloat16, device=x.device)
+        for b in range(B):
+            s_b = ops.gemm(_pad2d(q[b], T, Cp), _pad2d(k[b], Tp, Cp))                        # [T, Tp] scores
+            p_b = softmax_rows(s_b, float(C) ** -0.5, cols_valid=T)                           # zero beyond T
+            o_b = ops.gemm(p_b, _pad2d(v[b].t(), Cn, Tp))                                     # [T, Cn] = P V
+            o[b] = o_b[:, :C]
+        o = self._conv(p + "proj_out", o.view(B, H, W, C), with_bias=True)
+        return bias_add(o, None, x)
 
     @torch.no_grad()
     def decode_code(self, codebook_indices: torch.Tensor, shape=None) -> torch.Tensor:
@@ -205,9 +301,8 @@ class MagvitV2DecoderB200:
         if shape is not None and tuple(shape) != (int(round(codebook_indices.shape[1] ** 0.5)),) * 2:
             raise ValueError("only square token grids are supported")
         w = self.w
-        z = lfq_unpack(codebook_indices.to(self.device), self.codebook_dim)                      # [B,h,w,13]
-        h = _conv(z, w["post_quant_conv.weight"], w["post_quant_conv.bias"], 0)
-        h = _conv(h, w["conv_in.weight"], w["conv_in.bias"], 1)
+        z = lfq_postquant(codebook_indices.to(self.device), self.pq_w, self.pq_b, self.codebook_dim)   # [B,h,w,64]: 13 channels + zeros
+        h = self._conv("conv_in", z, with_bias=True)
         h = self._res("mid.block_1.", h)
         h = self._attn("mid.attn_1.", h)
         h = self._res("mid.block_2.", h)
@@ -221,8 +316,8 @@ class MagvitV2DecoderB200:
                 ready = emit
             if lvl != 0:
                 h = upsample2x(h)
-                h = bias_add(_conv(h, w[f"up.{lvl}.upsample.conv.weight"], None, 1), w[f"up.{lvl}.upsample.conv.bias"], emit_stats=True)
+                h = bias_add(self._conv(f"up.{lvl}.upsample.conv", h, with_bias=False), w[f"up.{lvl}.upsample.conv.bias"], emit_stats=True)
                 ready = True                 # ... and feeds norm1 of the next level's first block
         h = groupnorm_swish(h, w["norm_out.weight"], w["norm_out.bias"], out=h, stats_ready=ready)
-        h = _conv(h, w["conv_out.weight"], w["conv_out.bias"], 1)
-        return h.permute(0, 3, 1, 2).float()
+        h = self._conv("conv_out", h, with_bias=True)                  # 3 output channels: rows of the packed weight beyond 3 are zero,
+        return h.permute(0, 3, 1, 2).float()                           # the TMA store clips them

@@ -95,6 +95,45 @@ def test_bias_add_with_fused_groupnorm_statistics(dev):
             assert torch.equal(fused, plain) and torch.equal(y_fused, y_plain)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 32, 32, 512, 512, 3), (1, 64, 64, 256, 128, 3), (2, 16, 16, 64, 256, 3), (1, 8, 8, 32, 64, 3),
+                                              (3, 5, 7, 128, 128, 3), (1, 128, 128, 128, 8, 3), (2, 32, 32, 512, 256, 1), (1, 9, 33, 64, 32, 1),
+                                              (1, 32, 32, 64, 512, 3)])
+def test_conv_implicit_gemm_matches_torch(dev, B, H, W, Cin, Cout, k):
+    """ug_conv_nhwc_bf16 (tcgen05 implicit GEMM: 4-D TMA boxes per tap, borders / partial boxes / channel padding by TMA out-of-bounds
+    handling) against torch's fp32 convolution of the same bf16 values.  Tolerance: one bf16 rounding of an fp32-accumulated sum
+    (relative L2 <= 4e-3, max-abs <= 2^-6 max|ref|), as for the plain GEMM."""
+    from ml_unigen_b200 import magvit
+    g = torch.Generator(device=dev).manual_seed(B * 1000 + H + Cin + Cout + k)
+    x = torch.randn(B, H, W, Cin, device=dev, generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, device=dev, generator=g) * (Cin * k * k) ** -0.5).bfloat16()
+    b = torch.randn(Cout, device=dev, generator=g).bfloat16()
+    wp, bp = magvit.pack_conv(w.float(), b.float())
+    for with_bias in (True, False):
+        y = magvit.conv_nhwc(x, wp, bp if with_bias else None, Cout, k)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float() if with_bias else None, padding=k // 2).permute(0, 2, 3, 1)
+        d = y.float() - ref
+        assert y.shape == ref.shape
+        assert (d.norm() / ref.norm()).item() <= 4e-3, (d.norm() / ref.norm()).item()
+        assert d.abs().max().item() <= 2 ** -6 * ref.abs().max().item()
+
+
+def test_lfq_postquant_and_softmax_rows(dev):
+    from ml_unigen_b200 import magvit
+    g = torch.Generator(device=dev).manual_seed(4)
+    ids = torch.randint(0, 8192, (3, 256), device=dev, generator=g)
+    w = torch.randn(13, 13, device=dev, generator=g) * 0.3
+    b = torch.randn(13, device=dev, generator=g)
+    z = magvit.lfq_postquant(ids, w, b, 13, 64)
+    bits = MO.lfq_codebook_entry(ids.cpu()).permute(0, 2, 3, 1).to(dev)                  # [B,h,w,13] of +-1
+    ref = bits @ w.t() + b
+    assert z.shape == (3, 16, 16, 64) and int(z[..., 13:].abs().sum()) == 0
+    assert (z[..., :13].float() - ref).abs().max().item() <= 2e-2          # fp32 sums in a different order, one bf16 rounding
+    x = (torch.randn(300, 256, device=dev, generator=g) * 3).bfloat16()
+    y = magvit.softmax_rows(x, 0.7, cols_valid=200)
+    r = torch.softmax(0.7 * x[:, :200].float(), -1)
+    assert (y[:, :200].float() - r).abs().max().item() <= 2 ** -8 and int(y[:, 200:].abs().sum()) == 0
+
+
 def test_upsample2x_exact(dev):
     from ml_unigen_b200 import magvit
     x = torch.randn(2, 5, 7, 64, device=dev).bfloat16()
@@ -124,8 +163,7 @@ def test_decode_code_full_architecture_against_fp32_oracle(dev):
     dec = MagvitV2DecoderB200.random_init(dev, seed=3)
     ids = torch.randint(0, 8192, (2, 16), device=dev)
     out = dec.decode_code(ids)
-    sd = {k: v.float().contiguous() for k, v in dec.w.items()}
-    ref = MO.decode_code(sd, dec.num_res_blocks, ids)
+    ref = MO.decode_code(dec.raw, dec.num_res_blocks, ids)
     assert out.shape == ref.shape == (2, 3, 64, 64)
     rel = ((out - ref).norm() / ref.norm()).item()
     print(f"decode_code full arch: rel_l2={rel:.3e}")

@@ -32,7 +32,7 @@ def main():
     dec = MagvitV2DecoderB200.random_init(dev, seed=0)
     ids = torch.randint(0, 8192, (B, N), device=dev)
     t_own = timed(lambda: dec.decode_code(ids), 5)
-    sd_bf16 = {k: v.contiguous() for k, v in dec.w.items()}
+    sd_bf16 = {k: v.bfloat16().contiguous() for k, v in dec.raw.items()}
 
     def eager():
         with torch.no_grad():
