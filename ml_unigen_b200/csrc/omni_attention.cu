@@ -76,10 +76,6 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-// named barriers 2/3: the two softmax warpgroups take turns in the MUFU/FMA-heavy section, so that one tile's
-// softmax overlaps the OTHER tile's GEMMs instead of the other tile's softmax (ping-pong scheduling)
-__device__ __forceinline__ void turn_wait(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void turn_pass(int id) { asm volatile("bar.arrive %0, 256;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // executed by the whole (converged) MMA warp; one elected lane commits
@@ -217,6 +213,33 @@ __device__ __forceinline__ void tc_mma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, u
         "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
         : "memory");
 }
+// single-thread forms (the caller is the one thread elected by elect_one())
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_commit_1t(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss_1t(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts_1t(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+}
 // TS form: A operand (P, bf16 pairs) read from tensor memory, B from shared memory
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
@@ -224,6 +247,11 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void pin16(uint32_t (&v)[16])
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(v[i]));
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
 {
@@ -236,14 +264,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 
 
+#ifndef UG_ATTN_EARLYPUB
+#define UG_ATTN_EARLYPUB 0   // 1: hand a P half to the MMA warp right after its stores (waits for them); 0: behind the next half's first load
+#endif
 #ifndef UG_ATTN_POLY
 #define UG_ATTN_POLY 0       // of every 4 pairs of exponentials, how many go to the FMA pipe (polynomial); 0 = all on MUFU
-#endif
-#ifndef UG_ATTN_QK128
-#define UG_ATTN_QK128 0      // 1: S_x = Q_x K_t^T as ONE N = 128 MMA per k step (8 KB of operands per 64 cycles of math); 0: round 1's two
-#endif                       //    N = 64 halves (6 KB per 32 cycles: shared-memory bound, ~52 cycles each -- the MMA warp paced the kernel)
-#ifndef UG_ATTN_TURNS
-#define UG_ATTN_TURNS 0      // 1: the two softmax warpgroups alternate (named barriers), 0: free running
 #endif
 // 2^x for two values on the FMA pipe (round-to-nearest split x = n + f via the 1.5*2^23 constant, degree-3 minimax
 // polynomial for 2^f on [-0.5, 0.5] with relative error 7.5e-5 -- far below the bf16 rounding of P -- and an integer
@@ -349,7 +374,7 @@ constexpr uint32_t kOff2V = kOff2K + kKVStages * kTileBytes;
 constexpr uint32_t kOff2Bar = kOff2V + kKVStages * kTileBytes;
 constexpr uint32_t kOff2Items = kOff2Bar + 512;
 constexpr uint32_t kAttn2Smem = kOff2Items + 32 * 80 + 1024;
-constexpr int kAttn2Threads = 320;           // 2 softmax warpgroups (one per query tile) + TMA warp + MMA warp
+constexpr int kAttn2Threads = 384;           // 2 softmax warpgroups (one per query tile) + TMA warp + 2 MMA warps + a spare warp
 constexpr float kStaleSum = 65536.0f;         // a 64-column row sum above this means the softmax reference lags the scores by > ~10 bits
 
 struct ItemInfo {                 // one work item of the persistent grid, decoded once per CTA (see the kernel)
@@ -394,10 +419,10 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int L = p.a.L;
     if (tid == 0) {
         bar_init(&bars->q_full, 1);
-        bar_init(&bars->q_empty, 1);
+        bar_init(&bars->q_empty, 2);
         for (int s = 0; s < kKVStages; ++s) {
-            bar_init(&bars->k_full[s], 1); bar_init(&bars->k_empty[s], 1);
-            bar_init(&bars->v_full[s], 1); bar_init(&bars->v_empty[s], 1);
+            bar_init(&bars->k_full[s], 1); bar_init(&bars->k_empty[s], 2);
+            bar_init(&bars->v_full[s], 1); bar_init(&bars->v_empty[s], 2);
         }
         for (int x = 0; x < 2; ++x) {
             for (int hf = 0; hf < 2; ++hf) { bar_init(&bars->s_full[x][hf], 1); bar_init(&bars->p_full[x][hf], 128); }
@@ -579,118 +604,104 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             UG_TLI(0, 2);
         }
         __syncwarp();
-    } else if (warp == 9) {
-        // =========================================================== MMA issuer (one elected lane)
-        // Each query tile is pipelined in two 64-column halves: while a warpgroup is in the softmax of one half the
-        // tensor core computes the other half's P V and the next tile's Q K^T for the half just released, so the
-        // softmax warps and the tensor core both stay busy.  Slot order per kv tile: (A,0) (B,0) (A,1) (B,1); in
-        // each slot: O_x += P_x[half] V_t[half]  then  S_x[half] = Q_x K_(t+1)[half]^T.
+    } else if (warp == 9 || warp == 10) {
+        // =========================================================== MMA issuers: warp 9 drives query tile A, warp 10 tile B
+        // Every query tile is pipelined in two 64-key halves, each a chain of its own:
+        //     S_x[hf] = Q_x K_t[hf]^T  ->  softmax warpgroup x  ->  O_x += P_x[hf] V_t[hf]  ->  S_x[hf] = Q_x K_(t+1)[hf]^T  -> ...
+        // (the new scores go behind the P V that consumes the probabilities they overwrite).  While warpgroup x works on one
+        // half, the tensor core runs the other half's P V and next scores, so the warpgroup never waits for its own round trip.
+        // Round 1 served all four chains from ONE warp in a fixed order with per-instruction election: a ready chain waited
+        // for another chain's softmax and ~50 cycles of issue overhead per MMA made that warp the pacing role.  Now each query
+        // tile has its own issuing warp, and inside it ONE elected thread runs the whole chain (waits, MMAs, commits): in a
+        // region guarded by elect.sync ptxas keeps the MMA operands in uniform registers and the UTCHMMAs go out back to back.
+        // K/V stages and the Q tiles are handed back when BOTH warps have committed (barrier count 2); a warp whose tile does
+        // not need a kv tile just passes it on.
         {
-            constexpr uint32_t idesc_qk = make_idesc(kBM, UG_ATTN_QK128 ? kBN : 64, 0, 0);      // S tile (or half): M=128, N=128 (64)
-            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);        // O:      M=128, N=128, K=64 per half
-            const uint32_t qa_addr = s_u32(smem + kOff2QA), qb_addr = s_u32(smem + kOff2QB);
-            bool o_started[2] = {false, false};
-            const uint32_t q_lo[2] = {desc_lo_kmajor(qa_addr), desc_lo_kmajor(qb_addr)};
+            const int x = warp - 9;
+            constexpr uint32_t idesc_qk = make_idesc(kBM, 64, 0, 0);        // S half: M=128, N=64
+            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);        // O: M=128, N=128, K=64 per half
+            const uint32_t ql = desc_lo_kmajor(s_u32(smem + (x == 0 ? kOff2QA : kOff2QB)));
             const uint32_t k_lo0 = desc_lo_kmajor(s_u32(smem + kOff2K)), v_lo0 = desc_lo_mnmajor(s_u32(smem + kOff2V));
-            auto tile_on = [&](int x, int t) { return half_on(x, t, 0) || half_on(x, t, 1); };
-            // scores of kv tile t for query tile x: the whole 128-column tile (hf < 0) or one 64-column half
-            auto issue_qk = [&](int x, int t, int hf) {
-                const int j = jj + t - tU0, s = j % kKVStages;
-                // K tile: two 64-wide d panels of [128 kv rows x 128 B]; kv rows 64*hf.. start 8 KB into each panel
-                const uint32_t kl = k_lo0 + (uint32_t)s * (kTileBytes >> 4) + (uint32_t)(hf > 0 ? 1 : 0) * ((64u * 128u) >> 4);
-                const uint32_t ql = q_lo[x];
-                const uint32_t d = tmem + (uint32_t)x * 128u + (uint32_t)(hf > 0 ? 1 : 0) * 64u;
-#pragma unroll
-                for (int k = 0; k < kD / 16; ++k) {
-                    // 16 bf16 along d = 32 bytes inside the 128-byte swizzle row; panel switch at k = 4
-                    const uint32_t off = (uint32_t)(k >> 2) * (kPanelBytes >> 4) + (uint32_t)(k & 3) * 2u;
-                    tc_mma_ss_lo(d, ql + off, kl + off, idesc_qk, k > 0 ? 1u : 0u);
-                }
-                tc_commit(&bars->s_full[x][hf > 0 ? 1 : 0]);
-            };
-            auto wait_k = [&](int t) {
-                const int j = jj + t - tU0, s = j % kKVStages;
-                bar_wait(&bars->k_full[s], (uint32_t)(j / kKVStages) & 1u);
-                tc_fence_after();
-                return s;
-            };
-            auto last_pv = [&](int x, int t, int hf) {        // is (t, hf) the last half this tile accumulates?
-                return (hmask[x] >> (2 * (t - tU0) + hf + 1)) == 0ull;
-            };
-            if (lane == 0) UG_TLI(1, 0);
-            bar_wait(&bars->q_full, (uint32_t)n_items & 1u);
-            if (lane == 0) UG_TLI(1, 1);
-            {   // prologue: scores of the first kv tile (S_x is free: every P V of the previous item was issued before)
-                const int s = wait_k(tU0);
-                if (UG_ATTN_QK128) {
-                    for (int x = 0; x < 2; ++x)
-                        if (tile_on(x, tU0)) issue_qk(x, tU0, -1);
-                } else {
-                    for (int hf = 0; hf < 2; ++hf)
-                        for (int x = 0; x < 2; ++x)
-                            if (half_on(x, tU0, hf)) issue_qk(x, tU0, hf);
-                }
-                tc_commit(&bars->k_empty[s]);
-                if (tU0 + 1 >= tU1) tc_commit(&bars->q_empty);          // single kv tile: that was the last Q K^T of the item
-                if (lane == 0) UG_TLI(1, 2);
-            }
-            for (int t = tU0; t < tU1; ++t) {
-                const int j = jj + t - tU0, s = j % kKVStages;
-                const int jl = t - tU0;
-                const bool next = t + 1 < tU1;
-                int sn = 0;
-                bool v_ready = false, k_ready = false;
-                for (int hf = 0; hf < 2; ++hf) {
-                    for (int x = 0; x < 2; ++x) {
-                        if (half_on(x, t, hf)) {
-                            if (lane == 0) UG_TL(2, 4 * jl + 2 * hf + x, 0);
-                            bar_wait(&bars->p_full[x][hf], (uint32_t)np[x][hf] & 1u);
-                            if (lane == 0) UG_TL(2, 4 * jl + 2 * hf + x, 1);
-                            if (!v_ready) { bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u); v_ready = true; }
-                            if (!o_started[x] && cnt_x[x] > 0)           // O_x still holds the previous item until its epilogue has read it
-                                bar_wait(&bars->o_free[x], (uint32_t)(cnt_x[x] - 1) & 1u);
-                            tc_fence_after();
-                            // V tile rows 64*hf.. (MN-major): 16 kv rows per MMA
-                            const uint32_t vl = v_lo0 + (uint32_t)s * (kTileBytes >> 4) + (uint32_t)hf * ((64u * 128u) >> 4);
-                            const uint32_t p_tmem = tmem + (uint32_t)x * 128u + (uint32_t)hf * 64u;      // P half aliases its S half
-                            const uint32_t o_tmem = tmem + 256u + (uint32_t)x * 128u;
-                            const uint32_t acc0 = o_started[x] ? 1u : 0u;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                tc_mma_ts_lo(o_tmem, p_tmem + (uint32_t)k * 8u, vl + (uint32_t)k * ((16u * 128u) >> 4), idesc_pv,
-                                             k > 0 ? 1u : acc0);
-                            tc_commit(&bars->pv_done[x]);
-                            o_started[x] = true;
-                            ++np[x][hf];
-                            if (lane == 0) UG_TL(2, 4 * jl + 2 * hf + x, 2);
-                            if (last_pv(x, t, hf)) tc_commit(&bars->o_done[x]);
-                        }
-                        if (UG_ATTN_QK128) {
-                            // the whole next S_x tile overwrites both P halves of this one: it goes behind the LAST P V of (x, t)
-                            // (the tensor pipe executes in issue order); a tile without work yields its turn in the second half
-                            const bool last_here = half_on(x, t, 1) ? hf == 1 : (half_on(x, t, 0) ? hf == 0 : hf == 1);
-                            if (next && last_here && tile_on(x, t + 1)) {
-                                if (!k_ready) { sn = wait_k(t + 1); k_ready = true; }
-                                issue_qk(x, t + 1, -1);
-                                if (lane == 0) UG_TL(2, 4 * jl + 2 * hf + x, 3);
-                            }
-                        } else if (next && half_on(x, t + 1, hf)) {
-                            if (!k_ready) { sn = wait_k(t + 1); k_ready = true; }
-                            issue_qk(x, t + 1, hf);
-                            if (lane == 0) UG_TL(2, 4 * jl + 2 * hf + x, 3);
-                        }
+            const uint32_t s_tmem = tmem + (uint32_t)x * 128u, o_tmem = tmem + 256u + (uint32_t)x * 128u;
+            const unsigned long long hm = hmask[x];
+            const int nT = tU1 - tU0;
+            // the contiguous range [g0, ge) of 64-key halves (relative to kv tile tU0) that carry work for this query tile
+            const int g0 = hm ? __ffsll((long long)hm) - 1 : 0, ge = hm ? 64 - __clzll((long long)hm) : 0;
+            const int ta = hm ? g0 >> 1 : nT, tb = hm ? (ge - 1) >> 1 : nT - 1;      // its kv tiles [ta, tb]
+            uint32_t npl[2] = {(uint32_t)np[x][0], (uint32_t)np[x][1]};
+            if (elect_one()) {
+                // scores of half g (kv tile g >> 1, keys 64 * (g & 1) ..): 8 MMAs; hands the K stage back after the tile's last half
+                auto issue_qk = [&](int g) {
+                    const int tl_ = g >> 1, hf = g & 1;
+                    const int j = jj + tl_, s = j % kKVStages;
+                    if (g == g0 || hf == 0) {
+                        bar_wait(&bars->k_full[s], (uint32_t)(j / kKVStages) & 1u);
+                        tc_fence_after();
                     }
+                    // K tile: two 64-wide d panels of [128 kv rows x 128 B]; kv rows 64.. start 8 KB into each panel
+                    const uint32_t kl = k_lo0 + (uint32_t)s * (kTileBytes >> 4) + (uint32_t)hf * ((64u * 128u) >> 4);
+                    const uint32_t d = s_tmem + (uint32_t)hf * 64u;
+#pragma unroll
+                    for (int k = 0; k < kD / 16; ++k) {
+                        // 16 bf16 along d = 32 bytes inside the 128-byte swizzle row; panel switch at k = 4
+                        const uint32_t off = (uint32_t)(k >> 2) * (kPanelBytes >> 4) + (uint32_t)(k & 3) * 2u;
+                        tc_mma_ss_1t(d, ql + off, kl + off, idesc_qk, k > 0 ? 1u : 0u);
+                    }
+                    tc_commit_1t(&bars->s_full[x][hf]);
+                    if (hf == 1 || g + 1 == ge) tc_commit_1t(&bars->k_empty[s]);
+                    if (g + 1 == ge) tc_commit_1t(&bars->q_empty);            // the item's last Q K^T of this query tile
+                };
+                auto pass_on = [&](int tl_) {         // a kv tile this query tile does not need
+                    const int j = jj + tl_, s = j % kKVStages;
+                    const uint32_t ph = (uint32_t)(j / kKVStages) & 1u;
+                    bar_wait(&bars->k_full[s], ph);
+                    tc_commit_1t(&bars->k_empty[s]);
+                    bar_wait(&bars->v_full[s], ph);
+                    tc_commit_1t(&bars->v_empty[s]);
+                };
+                if (x == 0) UG_TLI(1, 0);
+                bar_wait(&bars->q_full, (uint32_t)n_items & 1u);
+                if (x == 0) UG_TLI(1, 1);
+                for (int tl_ = 0; tl_ < min(ta, nT); ++tl_) pass_on(tl_);
+                if (hm) {
+                    issue_qk(g0);
+                    if (g0 + 1 < ge) issue_qk(g0 + 1);
+                    if (x == 0) UG_TLI(1, 2);
+                    if (cnt_x[x] > 0) bar_wait(&bars->o_free[x], (uint32_t)(cnt_x[x] - 1) & 1u);   // O_x: the previous item's epilogue has read it
+                    for (int g = g0; g < ge; ++g) {
+                        const int tl_ = g >> 1, hf = g & 1;
+                        const int j = jj + tl_, s = j % kKVStages;
+                        if (x == 0) UG_TL(2, g - g0, 0);
+                        bar_wait(&bars->p_full[x][hf], npl[hf] & 1u);
+                        if (x == 0) UG_TL(2, g - g0, 1);
+                        if (g == g0 || hf == 0) bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u);
+                        tc_fence_after();
+                        // V tile rows 64*hf.. (MN-major): 16 kv rows per MMA; the P half aliases its S half
+                        const uint32_t vl = v_lo0 + (uint32_t)s * (kTileBytes >> 4) + (uint32_t)hf * ((64u * 128u) >> 4);
+                        const uint32_t p_tmem = s_tmem + (uint32_t)hf * 64u;
+                        const uint32_t acc0 = g > g0 ? 1u : 0u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_ts_1t(o_tmem, p_tmem + (uint32_t)k * 8u, vl + (uint32_t)k * ((16u * 128u) >> 4), idesc_pv, k > 0 ? 1u : acc0);
+                        tc_commit_1t(&bars->pv_done[x]);
+                        ++npl[hf];
+                        if (g + 1 == ge) tc_commit_1t(&bars->o_done[x]);
+                        if (hf == 1 || g + 1 == ge) tc_commit_1t(&bars->v_empty[s]);
+                        if (x == 0) UG_TL(2, g - g0, 2);
+                        if (g + 2 < ge) issue_qk(g + 2);
+                        if (x == 0) UG_TL(2, g - g0, 3);
+                    }
+                } else {
+                    tc_commit_1t(&bars->q_empty);
                 }
-                if (!v_ready) bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u);
-                tc_commit(&bars->v_empty[s]);
-                if (next) {
-                    if (!k_ready) sn = wait_k(t + 1);
-                    tc_commit(&bars->k_empty[sn]);
-                    if (t + 2 >= tU1) tc_commit(&bars->q_empty);        // the scores of the item's last kv tile are issued: Q may go
-                }
+                for (int tl_ = tb + 1; tl_ < nT; ++tl_) pass_on(tl_);
+                if (x == 0) UG_TLI(1, 3);
             }
-            if (lane == 0) UG_TLI(1, 3);
+            __syncwarp();
+            for (int g = g0; g < ge; ++g) ++np[x][g & 1];       // every lane keeps the books (phases of p_full)
         }
+    } else if (warp == 11) {
+        // spare warp (keeps the third warpgroup whole)
     } else {
         // =========================================================== softmax / correction / epilogue, one warpgroup per query tile
         const int x = warp >> 2;                         // 0: tile A, 1: tile B
@@ -713,121 +724,130 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             const int max_lo = (i1 > P) ? P : 0;
             const int min_hi = (i0 < S) ? (i0 + 1) : L;
             const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-            const uint32_t s_addr = tmem + lane_base + (uint32_t)x * 128u;      // S_x, and P_x in its first 64 columns
+            const uint32_t s_addr = tmem + lane_base + (uint32_t)x * 128u;      // S_x; P_x half hf in the first 32 columns of S half hf
             const uint32_t o_addr = tmem + lane_base + 256u + (uint32_t)x * 128u;
             const float c = p.scale_log2;
             float m_ref = -INFINITY;                     // the (possibly stale) max the exponentials are taken against
             float l_run = 0.0f;
             const bool dump = p.dbg && x == 0 && qp == 0 && h == 0 && b == 0;
-
             bool o_live = false;                          // O_x holds (or is about to hold) an accumulation of THIS item
+
+            // Optimistic online softmax: the exponentials of a 64-column half are taken against the current reference m_ref
+            // without looking for the row max first (any reference is exact as long as O, l and P share it).  The row sum of
+            // the half tells whether the reference went stale (sum > 2^16, inf/NaN, or no reference yet); only then -- the
+            // first half of a row and after rare jumps of the scores -- slow_half() reloads the scores, takes the true max,
+            // rescales O and l and redoes the half.
+            auto slow_half = [&](uint32_t sh_addr, bool full, int clo, int chi, bool stale, uint32_t (&pa)[16], uint32_t (&pb)[16],
+                                 float& alpha) -> float {
+                uint32_t w0[32], w1[32];
+                tmem_ld32_async(sh_addr, w0);
+                tmem_ld32_async(sh_addr + 32, w1);
+                tmem_ld_wait();
+                pin32(w0); pin32(w1);
+                float mx = -INFINITY;
+                if (full) { mx = row_max_chunk<false>(w0, 0, clo, chi, mx); mx = row_max_chunk<false>(w1, 32, clo, chi, mx); }
+                else { mx = row_max_chunk<true>(w0, 0, clo, chi, mx); mx = row_max_chunk<true>(w1, 32, clo, chi, mx); }
+                const float m_true = fmaxf(m_ref, mx * c);
+                const float m_new = stale ? m_true : m_ref;                  // rows that are fine keep their reference
+                const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
+                alpha = (m_new != m_ref) ? ex2(m_ref - m_use) : 1.0f;        // 0 when there was no reference yet
+                // O_x may only be rescaled when no P V of this tile is in flight.  The scores of this kv tile were issued behind
+                // every P V of the previous one, so only the P V of the half published just before (half 0 of this kv tile, when
+                // this is half 1) can still be running: wait for its phase of pv_done (the barrier is at most one phase behind,
+                // so the parity wait is exact).
+                if (o_live) {
+                    bar_wait(&bars->pv_done[x], (uint32_t)(n_pub - 1) & 1u);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld32(o_addr + ch * 32, v);
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) * alpha);
+                        tmem_st32(o_addr + ch * 32, v);
+                    }
+                }
+                float rs;
+                if (full) rs = prob_chunk<false>(w0, pa, c, m_use, 0, clo, chi) + prob_chunk<false>(w1, pb, c, m_use, 32, clo, chi);
+                else rs = prob_chunk<true>(w0, pa, c, m_use, 0, clo, chi) + prob_chunk<true>(w1, pb, c, m_use, 32, clo, chi);
+                m_ref = m_new;
+                return rs;
+            };
+            // the P half is in tensor memory: hand it to the MMA warp
+            auto publish = [&](int hf) {
+                tmem_st_wait();
+                tc_fence_before();
+                bar_arrive(&bars->p_full[x][hf]);
+                o_live = true;
+                ++n_pub;
+            };
+            auto dump_p = [&](int hf, const uint32_t (&pa)[16], const uint32_t (&pb)[16]) {
+                for (int q = 0; q < 16; ++q) {
+                    p.dbg[16384 + r * 128 + hf * 64 + 2 * q] = __uint_as_float(pa[q] << 16);
+                    p.dbg[16384 + r * 128 + hf * 64 + 2 * q + 1] = __uint_as_float(pa[q] & 0xffff0000u);
+                    p.dbg[16384 + r * 128 + hf * 64 + 32 + 2 * q] = __uint_as_float(pb[q] << 16);
+                    p.dbg[16384 + r * 128 + hf * 64 + 32 + 2 * q + 1] = __uint_as_float(pb[q] & 0xffff0000u);
+                }
+            };
+
             if (r == 0) UG_TLI(2 + x, 0);
+            int pend = -1;               // half whose P stores are in flight and not yet handed to the MMA warp
+            int n = 0;
             for (int t = t0; t < t1; ++t) {
-              if (UG_ATTN_QK128 && (half_on(x, t, 0) || half_on(x, t, 1))) {      // the scores of the whole tile land at once
-                  bar_wait(&bars->s_full[x][0], (uint32_t)ns[0] & 1u);
-                  ++ns[0];
-              }
               for (int hf = 0; hf < 2; ++hf) {
                 if (!half_on(x, t, hf)) continue;
-                const int n = 2 * (t - t0) + hf;
                 const int j0 = t * kBN + hf * 64 + kv_off;
-                const bool full_tile = (j0 >= max_lo) && (j0 + 64 <= min_hi);
+                const bool full = (j0 >= max_lo) && (j0 + 64 <= min_hi);
                 const int clo = lo - j0, chi = hi - j0;
                 const uint32_t sh_addr = s_addr + (uint32_t)hf * 64u;
                 if (r == 0) UG_TL(x, n, 0);
-                if (!UG_ATTN_QK128) {
-                    bar_wait(&bars->s_full[x][hf], (uint32_t)ns[hf] & 1u);
-                    ++ns[hf];
-                }
+                bar_wait(&bars->s_full[x][hf], (uint32_t)ns[hf] & 1u);
+                ++ns[hf];
                 tc_fence_after();
                 if (r == 0) UG_TL(x, n, 1);
-                // 64 scores of this row come to registers: two loads in flight, one wait
-                uint32_t v0[32], v1[32];
-                tmem_ld32_async(sh_addr, v0);
-                tmem_ld32_async(sh_addr + 32, v1);
-                tmem_ld_wait();
-                pin32(v0); pin32(v1);
-                if (r == 0) UG_TL(x, n, 6);
-                if (dump && t == t0)
-                    for (int q = 0; q < 32; ++q) {
-                        p.dbg[r * 128 + hf * 64 + q] = __uint_as_float(v0[q]);
-                        p.dbg[r * 128 + hf * 64 + 32 + q] = __uint_as_float(v1[q]);
-                    }
-                // Optimistic online softmax: the exponentials are taken against the current reference m_ref without
-                // looking for the row max first (any reference is exact as long as O, l and P share it).  The row sum
-                // of the half tells whether the reference went stale (sum > 2^16, inf/NaN, or no reference yet); only
-                // then -- the first half of a row and after rare jumps of the scores -- the true max is computed, O and
-                // l are rescaled and the half is redone.  This removes the max pass and its latency from the hot path.
+                // Scores come to registers 32 columns at a time, each load in flight while something else happens: the first one
+                // while the PREVIOUS half's probabilities are handed over (wait for their tensor-memory stores, fence, arrive), the
+                // second one while the first chunk is in the MUFU section.  (tcgen05.wait::ld waits for ALL loads of the thread, so a
+                // load is issued right after the wait for its predecessor; pin16 keeps ptxas from sinking the arithmetic below it.)
+                uint32_t va[32], vb[32];
                 uint32_t pk0[16], pk1[16];
+                tmem_ld32_async(sh_addr, va);
+                if (pend >= 0) publish(pend);
+                tmem_ld_wait();
+                pin32(va);
+                tmem_ld32_async(sh_addr + 32, vb);
+                if (r == 0) UG_TL(x, n, 2);
+                if (dump && t == t0)
+                    for (int q = 0; q < 32; ++q) p.dbg[r * 128 + hf * 64 + q] = __uint_as_float(va[q]);
                 float rs = 0.0f, alpha = 1.0f;
                 bool stale = (m_ref == -INFINITY);
-                if (!__any_sync(0xffffffffu, stale)) {
-                    if (full_tile) {
-                        rs = prob_chunk<false>(v0, pk0, c, m_ref, 0, clo, chi) + prob_chunk<false>(v1, pk1, c, m_ref, 32, clo, chi);
-                    } else {
-                        rs = prob_chunk<true>(v0, pk0, c, m_ref, 0, clo, chi) + prob_chunk<true>(v1, pk1, c, m_ref, 32, clo, chi);
-                    }
-                    stale = !(rs <= kStaleSum);
+                const bool opt = !__any_sync(0xffffffffu, stale);
+                if (opt) {
+                    rs = full ? prob_chunk<false>(va, pk0, c, m_ref, 0, clo, chi) : prob_chunk<true>(va, pk0, c, m_ref, 0, clo, chi);
+                    pin16(pk0);
                 }
-                if (r == 0) UG_TL(x, n, 2);
-                if (__any_sync(0xffffffffu, stale)) {
-                    float mx = -INFINITY;
-                    if (full_tile) {
-                        mx = row_max_chunk<false>(v0, 0, clo, chi, mx);
-                        mx = row_max_chunk<false>(v1, 32, clo, chi, mx);
-                    } else {
-                        mx = row_max_chunk<true>(v0, 0, clo, chi, mx);
-                        mx = row_max_chunk<true>(v1, 32, clo, chi, mx);
-                    }
-                    const float m_true = fmaxf(m_ref, mx * c);
-                    const float m_new = stale ? m_true : m_ref;                  // rows that are fine keep their reference
-                    const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
-                    alpha = (m_new != m_ref) ? ex2(m_ref - m_use) : 1.0f;        // 0 when there was no reference yet
-                    // O_x may only be rescaled when no P V of this tile is in flight.  These scores (half number n_pub
-                    // of this tile) were issued behind the P V of half n_pub-2, so everything up to n_pub-2 is complete;
-                    // only the P V of the half published just before can still be running: wait for its phase of
-                    // pv_done (the barrier is at most one phase behind, so the parity wait is exact).
-                    if (o_live) {
-                        bar_wait(&bars->pv_done[x], (uint32_t)(n_pub - 1) & 1u);
-                        tc_fence_after();
-#pragma unroll 1
-                        for (int ch = 0; ch < 4; ++ch) {
-                            uint32_t v[32];
-                            tmem_ld32(o_addr + ch * 32, v);
-#pragma unroll
-                            for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) * alpha);
-                            tmem_st32(o_addr + ch * 32, v);
-                        }
-                    }
-                    if (full_tile) {
-                        rs = prob_chunk<false>(v0, pk0, c, m_use, 0, clo, chi) + prob_chunk<false>(v1, pk1, c, m_use, 32, clo, chi);
-                    } else {
-                        rs = prob_chunk<true>(v0, pk0, c, m_use, 0, clo, chi) + prob_chunk<true>(v1, pk1, c, m_use, 32, clo, chi);
-                    }
-                    m_ref = m_new;
-                }
+                tmem_ld_wait();
+                pin32(vb);
                 if (r == 0) UG_TL(x, n, 3);
                 if (dump && t == t0)
-                    for (int q = 0; q < 16; ++q) {
-                        p.dbg[16384 + r * 128 + hf * 64 + 2 * q] = __uint_as_float(pk0[q] << 16);
-                        p.dbg[16384 + r * 128 + hf * 64 + 2 * q + 1] = __uint_as_float(pk0[q] & 0xffff0000u);
-                        p.dbg[16384 + r * 128 + hf * 64 + 32 + 2 * q] = __uint_as_float(pk1[q] << 16);
-                        p.dbg[16384 + r * 128 + hf * 64 + 32 + 2 * q + 1] = __uint_as_float(pk1[q] & 0xffff0000u);
-                    }
+                    for (int q = 0; q < 32; ++q) p.dbg[r * 128 + hf * 64 + 32 + q] = __uint_as_float(vb[q]);
+                if (opt) {
+                    rs += full ? prob_chunk<false>(vb, pk1, c, m_ref, 32, clo, chi) : prob_chunk<true>(vb, pk1, c, m_ref, 32, clo, chi);
+                    stale = !(rs <= kStaleSum);
+                }
+                if (__any_sync(0xffffffffu, stale)) rs = slow_half(sh_addr, full, clo, chi, stale, pk0, pk1, alpha);
+                if (dump && t == t0) dump_p(hf, pk0, pk1);
                 // P half -> tensor memory (A operand of the second GEMM), over the score columns already consumed
                 tmem_st16(sh_addr, pk0);
                 tmem_st16(sh_addr + 16, pk1);
-                if (r == 0) UG_TL(x, n, 7);
-                tmem_st_wait();
-                if (r == 0) UG_TL(x, n, 4);
                 l_run = l_run * alpha + rs;
-                o_live = true;
-                ++n_pub;
-                tc_fence_before();
-                bar_arrive(&bars->p_full[x][hf]);
-                if (r == 0) UG_TL(x, n, 5);
+                if (UG_ATTN_EARLYPUB) publish(hf);
+                else pend = hf;
+                if (r == 0) UG_TL(x, n, 4);
+                ++n;
               }
             }
+            if (pend >= 0) publish(pend);
             // epilogue: O / l -> bf16 -> global
             if (r == 0) UG_TLI(2 + x, 1);
             bar_wait(&bars->o_done[x], (uint32_t)cnt_x[x] & 1u);

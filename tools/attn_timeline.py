@@ -20,12 +20,12 @@ torch.cuda.synchronize()
 t = dump[32768:].cpu().view(4, 64, 8)
 names = {0: "softmaxA", 1: "softmaxB", 2: "mma"}
 for role in (0, 1):
-    print(names[role], "events: wait_start, s_full, max_done, rescale_done, st_wait_done, arrived, chunk0_done, chunk1_issued")
-    for it in range(12):
-        print(it, [int(x) for x in t[role, it, :8].tolist()])
-print("mma (tile A issuer) events per (kv tile, half): wait_start, p_full, pv_issued, qk_issued")
-for it in range(24):
-    print(it // 2, it % 2, [int(x) for x in t[2, it, :4].tolist()])
+    print(names[role], "events per 64-key half: wait_start, s_full, chunk0_loaded (previous half published), chunk1_loaded, P stored")
+    for it in range(22):
+        print(it, [int(x) for x in t[role, it, :5].tolist()])
+print("mma warp of tile A, per half: wait_start, p_full, pv_issued, next_qk_issued")
+for it in range(22):
+    print(it, [int(x) for x in t[2, it, :4].tolist()])
 
 ti = dump[32768 + 1536:].cpu().view(4, 16, 8)
 print("item boundaries of CTA 0 (persistent grid): producer [start, q_empty ok, loads issued] | mma [start, q_full, first QK issued, done] | softmax A/B [start, wait o_done, o_done, o_free]")
