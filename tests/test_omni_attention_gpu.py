@@ -67,6 +67,13 @@ def _diagnose(q, k, dump, P, S, scale):
     (2, 258, [0, 40], [100, 257]),             # L % 256 = 2: GQA-packed tail tile (2 rows x 6 heads in one tile); causal + bidirectional rows in it
     (2, 533, [3, 0], [200, 520]),              # L % 256 = 21: the largest packed tail (126 rows)
     (1, 534, [0], [300]),                      # L % 256 = 22: too many rows to pack, ordinary tail tile
+    # BASELINE config 4 (S in {128, 256, 512}, P in {0, S/2}, N in {256, 1024}; L = S + N + 2): the shapes the sweep TIMES
+    (2, 386, [0, 64], [128, 128]),             # S = 128, N = 256
+    (2, 514, [0, 128], [256, 256]),            # S = 256, N = 256
+    (2, 770, [0, 256], [512, 512]),            # S = 512, N = 256
+    (2, 1154, [0, 64], [128, 128]),            # S = 128, N = 1024
+    (2, 1282, [0, 128], [256, 256]),           # S = 256, N = 1024
+    (2, 1538, [0, 256], [512, 512]),           # S = 512, N = 1024
 ])
 def test_omni_attention_matches_fp32_reference(dev, B, L, P, S):
     from ml_unigen_b200 import ops, _lib
