@@ -458,9 +458,11 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // running state of the roles across items (every thread walks the same item sequence)
     int n_items = 0;                                  // items started by this CTA: phase of q_full / q_empty
     int jj = 0;                                       // kv tiles of the items before this one: stage and phase of the K/V rings
-    int cnt_x[2] = {0, 0};                            // items in which query tile x carried work: phase of o_done / o_free
-    int np[2][2] = {{0, 0}, {0, 0}};                  // MMA warp: P halves consumed (phase of p_full)
-    int ns[2] = {0, 0};                               // softmax: halves (QK128: tiles, in ns[0]) processed (phase of s_full)
+    // (scalars, not arrays: dynamically indexed arrays live in local memory, and a dependent load/store round trip per counter update
+    //  -- ~250 cycles each -- kept the MMA warp 6 k cycles between two items and cost the softmax threads ~300 cycles per half)
+    int cnt_x0 = 0, cnt_x1 = 0;                       // items in which query tile 0 / 1 carried work: phase of o_done / o_free
+    int np_0 = 0, np_1 = 0;                           // MMA warp of tile x: P halves 0 / 1 consumed (phase of p_full[x][hf])
+    int ns_0 = 0, ns_1 = 0;                           // softmax warpgroup x: score halves 0 / 1 processed (phase of s_full[x][hf])
     int n_pub = 0;                                    // softmax: P halves published so far by this warpgroup (phase of pv_done)
 
     // Item list, heaviest first, walked round-robin by the CTAs (a static schedule: items of one class cost the same up to the
@@ -552,8 +554,8 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int hk = h / G;
     const int iA = q0 + lA, iB = q0 + lB;
     const int tA0 = it.tA0, tA1 = it.tA1, tB0 = it.tB0, tB1 = it.tB1, tU0 = it.tU0, tU1 = it.tU1, kv_off = it.kv_off;
-    const unsigned long long hmask[2] = {it.hmask[0], it.hmask[1]};
-    auto half_on = [&](int x, int t, int hf) -> bool { return (hmask[x] >> (2 * (t - tU0) + hf)) & 1ull; };
+    const unsigned long long hmask0 = it.hmask[0], hmask1 = it.hmask[1];
+    auto half_on = [&](int x, int t, int hf) -> bool { return ((x ? hmask1 : hmask0) >> (2 * (t - tU0) + hf)) & 1ull; };
     tl = p.dbg && blockIdx.x == 0 && n_items == 0;
     // item-boundary stamps of CTA 0 (test hook): dbg[32768 + 1536 + role * 128 + item * 8 + event], 16 items, 4 roles
     const bool tli = p.dbg && blockIdx.x == 0 && n_items < 16;
@@ -623,12 +625,13 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             const uint32_t ql = desc_lo_kmajor(s_u32(smem + (x == 0 ? kOff2QA : kOff2QB)));
             const uint32_t k_lo0 = desc_lo_kmajor(s_u32(smem + kOff2K)), v_lo0 = desc_lo_mnmajor(s_u32(smem + kOff2V));
             const uint32_t s_tmem = tmem + (uint32_t)x * 128u, o_tmem = tmem + 256u + (uint32_t)x * 128u;
-            const unsigned long long hm = hmask[x];
+            const unsigned long long hm = x ? hmask1 : hmask0;
             const int nT = tU1 - tU0;
             // the contiguous range [g0, ge) of 64-key halves (relative to kv tile tU0) that carry work for this query tile
             const int g0 = hm ? __ffsll((long long)hm) - 1 : 0, ge = hm ? 64 - __clzll((long long)hm) : 0;
             const int ta = hm ? g0 >> 1 : nT, tb = hm ? (ge - 1) >> 1 : nT - 1;      // its kv tiles [ta, tb]
-            uint32_t npl[2] = {(uint32_t)np[x][0], (uint32_t)np[x][1]};
+            uint32_t npl0 = (uint32_t)np_0, npl1 = (uint32_t)np_1;
+            const int cnt_me = x == 0 ? cnt_x0 : cnt_x1;
             if (elect_one()) {
                 // scores of half g (kv tile g >> 1, keys 64 * (g & 1) ..): 8 MMAs; hands the K stage back after the tile's last half
                 auto issue_qk = [&](int g) {
@@ -667,12 +670,12 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     issue_qk(g0);
                     if (g0 + 1 < ge) issue_qk(g0 + 1);
                     if (x == 0) UG_TLI(1, 2);
-                    if (cnt_x[x] > 0) bar_wait(&bars->o_free[x], (uint32_t)(cnt_x[x] - 1) & 1u);   // O_x: the previous item's epilogue has read it
+                    if (cnt_me > 0) bar_wait(&bars->o_free[x], (uint32_t)(cnt_me - 1) & 1u);   // O_x: the previous item's epilogue has read it
                     for (int g = g0; g < ge; ++g) {
                         const int tl_ = g >> 1, hf = g & 1;
                         const int j = jj + tl_, s = j % kKVStages;
                         if (x == 0) UG_TL(2, g - g0, 0);
-                        bar_wait(&bars->p_full[x][hf], npl[hf] & 1u);
+                        bar_wait(&bars->p_full[x][hf], (hf ? npl1 : npl0) & 1u);
                         if (x == 0) UG_TL(2, g - g0, 1);
                         if (g == g0 || hf == 0) bar_wait(&bars->v_full[s], (uint32_t)(j / kKVStages) & 1u);
                         tc_fence_after();
@@ -684,7 +687,7 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                         for (int k = 0; k < 4; ++k)
                             tc_mma_ts_1t(o_tmem, p_tmem + (uint32_t)k * 8u, vl + (uint32_t)k * ((16u * 128u) >> 4), idesc_pv, k > 0 ? 1u : acc0);
                         tc_commit_1t(&bars->pv_done[x]);
-                        ++npl[hf];
+                        if (hf) ++npl1; else ++npl0;
                         if (g + 1 == ge) tc_commit_1t(&bars->o_done[x]);
                         if (hf == 1 || g + 1 == ge) tc_commit_1t(&bars->v_empty[s]);
                         if (x == 0) UG_TL(2, g - g0, 2);
@@ -698,7 +701,8 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 if (x == 0) UG_TLI(1, 3);
             }
             __syncwarp();
-            for (int g = g0; g < ge; ++g) ++np[x][g & 1];       // every lane keeps the books (phases of p_full)
+            np_0 += ((ge + 1) >> 1) - ((g0 + 1) >> 1);          // every lane keeps the books (phases of p_full): even and odd g in [g0, ge)
+            np_1 += (ge >> 1) - (g0 >> 1);
         }
     } else if (warp == 11) {
         // spare warp (keeps the third warpgroup whole)
@@ -801,8 +805,8 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 const int clo = lo - j0, chi = hi - j0;
                 const uint32_t sh_addr = s_addr + (uint32_t)hf * 64u;
                 if (r == 0) UG_TL(x, n, 0);
-                bar_wait(&bars->s_full[x][hf], (uint32_t)ns[hf] & 1u);
-                ++ns[hf];
+                bar_wait(&bars->s_full[x][hf], (uint32_t)(hf ? ns_1 : ns_0) & 1u);
+                if (hf) ++ns_1; else ++ns_0;
                 tc_fence_after();
                 if (r == 0) UG_TL(x, n, 1);
                 // Scores come to registers 32 columns at a time, each load in flight while something else happens: the first one
@@ -850,7 +854,7 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             if (pend >= 0) publish(pend);
             // epilogue: O / l -> bf16 -> global
             if (r == 0) UG_TLI(2 + x, 1);
-            bar_wait(&bars->o_done[x], (uint32_t)cnt_x[x] & 1u);
+            bar_wait(&bars->o_done[x], (uint32_t)(x == 0 ? cnt_x0 : cnt_x1) & 1u);
             if (r == 0) UG_TLI(2 + x, 2);
             tc_fence_after();
             const float inv_l = 1.0f / l_run;
@@ -878,8 +882,8 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
     // every thread keeps the same books
     jj += tU1 - tU0;
-    cnt_x[0] += 1;
-    cnt_x[1] += hasB ? 1 : 0;
+    cnt_x0 += 1;
+    cnt_x1 += hasB ? 1 : 0;
     ++n_items;
     }       // items of the table
     }       // tables
