@@ -265,16 +265,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 
 
 #ifndef UG_ATTN_EARLYPUB
-#define UG_ATTN_EARLYPUB 0   // 1: hand a P half to the MMA warp right after its stores (waits for them); 0: behind the next half's first load
+#define UG_ATTN_EARLYPUB 1   // 1: hand a P half to the MMA warp right after its stores (waits for them); 0: behind the next half's first load
+                             //    (round 2, after the counters left local memory: 1 is 1-2 % faster; it was a wash before)
 #endif
 #ifndef UG_ATTN_POLY
-#define UG_ATTN_POLY 0       // of every 4 pairs of exponentials, how many go to the FMA pipe (polynomial); 0 = all on MUFU
+#define UG_ATTN_POLY 1       // of every 4 pairs of exponentials, how many go to the FMA pipe (polynomial); 0 = all on MUFU
+                             //    (round 2: 1 = a quarter of the exponentials: window pass 0.173 -> 0.164 ms; 2 is slower again: FMA issue)
 #endif
 // 2^x for two values on the FMA pipe (round-to-nearest split x = n + f via the 1.5*2^23 constant, degree-3 minimax
 // polynomial for 2^f on [-0.5, 0.5] with relative error 7.5e-5 -- far below the bf16 rounding of P -- and an integer
-// add of n into the exponent).  MUFU.EX2 is the scarcest pipe of this kernel on B200 (measured ~16 cycles per warp
-// instruction: 128x128 exponentials per tile cost twice the tensor-core time of the two GEMMs), so most exponentials
-// are computed here and only a fraction goes to the MUFU.
+// add of n into the exponent).  MUFU.EX2 costs 8 cycles per warp instruction and sub-partition, and the two warpgroups share it:
+// the exponentials of a kv tile take as long as its tensor-core work.  A quarter of them (UG_ATTN_POLY = 1) is computed here;
+// a larger share loses again to the extra FMA-pipe instructions (measured).
 __device__ __forceinline__ float2 ex2_poly2(float2 x)
 {
     const float2 magic = make_float2(12582912.0f, 12582912.0f);

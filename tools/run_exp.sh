@@ -1,3 +1,2 @@
-timeout 600 python -m pytest tests/test_omni_attention_gpu.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/exp_pytest.log
-NO_SDPA=1 timeout 300 python tools/bench_attention.py > gpurun_out/exp_bench.log 2>&1
-timeout 120 python tools/attn_timeline.py > gpurun_out/tl_x.txt 2>&1
+timeout 900 python -m pytest tests/test_decode_step_gpu.py tests/test_pipeline_gpu.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/exp_pytest.log
+BS=1,16,64,128 timeout 300 python tools/bench_decode.py > gpurun_out/exp_decode.log 2>&1
