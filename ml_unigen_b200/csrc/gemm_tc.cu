@@ -168,17 +168,54 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+#ifndef UG_GEMM_L2HINT
+#define UG_GEMM_L2HINT 1     // 1: the weight tiles are loaded with an L2 evict_last policy and the output tiles stored with evict_first
+#endif
+// L2 cache policies (createpolicy): the output of a launch (294 MB for gate|up) streams through L2 once and is not read back by
+// this kernel, while W (55 MB) is swept by every round of tiles -- without a hint the stores evict W and it is fetched from HBM
+// several times per launch (ncu: 456 MB read against 105 MB of operands)
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3)
 {
+#if UG_GEMM_L2HINT
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(c3), "l"(l2_policy_evict_first())
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                  "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1)
 {
+#if UG_GEMM_L2HINT
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1), "l"(l2_policy_evict_first())
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                  "r"(c1)
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -352,6 +389,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         // =========================================================== TMA producer (one lane, in both CTAs)
         if (lane == 0) {
             uint32_t it = 0;
+#if UG_GEMM_L2HINT
+            const uint64_t w_policy = l2_policy_evict_last();
+#endif
             for (int ui = 0; ui < n_units; ++ui) {
                 int mb, nb, half;
                 unit(ui, mb, nb, half);
@@ -382,7 +422,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     } else {
                         tma_load_2d_pair(dst, &tm_a, fb, kb * kGK, m0);
                     }
+#if UG_GEMM_L2HINT
+                    tma_load_2d_pair_hint(dst + kABytes, wmap, fb, kb * kGK, n0, w_policy);
+#else
                     tma_load_2d_pair(dst + kABytes, wmap, fb, kb * kGK, n0);
+#endif
                 }
             }
         }

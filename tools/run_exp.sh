@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_decode_step_gpu.py tests/test_pipeline_gpu.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/exp_pytest.log
-BS=1,16,64,128 timeout 300 python tools/bench_decode.py > gpurun_out/exp_decode.log 2>&1
+ncu --set full --clock-control none --import-source on -f -k regex:gemm_tc_kernel --launch-skip 2 -c 1 -o gpurun_out/ncu_gemm_swiglu_r2 python tools/prof_gemm.py gate_up > gpurun_out/ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -f -k regex:gemm_tc_kernel --launch-skip 2 -c 1 -o gpurun_out/ncu_gemm_downres_r2 python tools/prof_gemm.py down_res > gpurun_out/ncu2.log 2>&1
