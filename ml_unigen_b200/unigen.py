@@ -30,7 +30,7 @@ from .sampling import cosine_schedule
 class _StepGraph:
     """The per-step backbone pass of the prefix-reuse path (embed the N+2 image-block rows, 28 layers, final norm, codebook
     head) as ONE CUDA graph over static buffers.  Every launch inside it is a plain asynchronous kernel launch, so the
-    ~200 launches of a MaskGIT step replay without CPU work and with the launch-to-launch gaps of a graph."""
+    142 launches of a MaskGIT step replay without CPU work and with the launch-to-launch gaps of a graph."""
 
     def __init__(self, bb: QwenBackboneB200, n_seq: int, L: int, N: int, s0: int, V: int, text_vocab: int):
         dev = bb.device
