@@ -246,6 +246,64 @@ def reference_decode_ops_gpu(torch, dev, B, N=1024, V=8192, iters=5):
     return (time.perf_counter() - t0) / iters * 1e3
 
 
+def isolated_decode_points(torch, dev, ops, hbm_peak, N=1024, V=8192, batches=(16, 64, 128), iters=20):
+    """BASELINE.json configs[2] in brief (the full sweep: tools/bench_decode.py -> profiles/r2_decode_sweep.json): the decode step
+    alone on synthetic flat logits (0.02 * randn: what a random-init model produces), all rows masked, in-kernel Philox, CUDA events
+    around both launches, logits larger than L2 or L2 flushed between iterations."""
+    out = []
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for Bq in batches:
+        g = torch.Generator(device=dev).manual_seed(0)
+        logits = (0.02 * torch.randn(Bq, N, V, device=dev, generator=g)).bfloat16()
+        ws = ops.DecodeWorkspace(Bq, N, V, dev)
+        ids0 = torch.full((Bq, N), 159866, dtype=torch.int64, device=dev)
+        ids = ids0.clone()
+        ms = []
+        for it in range(iters + 3):
+            ids.copy_(ids0)
+            if Bq * N * V * 2 < 300e6:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(300000)              # the GPU is busy while the host enqueues: no launch gap inside the events
+            e0.record()
+            ops.decode_step(logits, ids, mask_token_id=159866, mask_len_cap=1020, temperature=0.5, workspace=ws, seed=1, offset=it)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                ms.append(e0.elapsed_time(e1))
+        ms.sort()
+        t = ms[len(ms) // 2] * 1e-3
+        out.append({"B": Bq, "us": t * 1e6, "GB/s": Bq * N * V * 2 / t / 1e9, "frac": Bq * N * V * 2 / t / 1e9 / hbm_peak})
+        del logits, ws
+    del flush
+    return out
+
+
+def isolated_attention_point(torch, dev, ops, peak_tf, B=16, S=137, N=1024, Hq=12, Hkv=2, D=128, iters=28):
+    """BASELINE.json configs[3] in brief (the full sweep: tools/bench_attention.py -> profiles/r2_attention_sweep.json): the
+    per-step window pass of config 2 (N + 2 query rows x all L keys, P = 0) alone, 28 launches back to back, CUDA events."""
+    L = S + N + 2
+    g = torch.Generator(device=dev).manual_seed(0)
+    q = torch.randn(B, L - S, Hq, D, device=dev, generator=g).bfloat16()
+    k = torch.randn(B, L, Hkv, D, device=dev, generator=g).bfloat16()
+    v = torch.randn(B, L, Hkv, D, device=dev, generator=g).bfloat16()
+    P = torch.zeros(B, dtype=torch.int32, device=dev)
+    St = torch.full((B,), S, dtype=torch.int32, device=dev)
+    o = torch.empty_like(q)
+    for _ in range(5):
+        ops.omni_attention(q, k, v, P, St, D ** -0.5, out=o, q_offset=S)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        ops.omni_attention(q, k, v, P, St, D ** -0.5, out=o, q_offset=S)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / iters
+    fl = 4 * D * Hq * B * (N + 2) * L
+    return {"ms": t * 1e3, "TFLOP/s": fl / t / 1e12, "frac": fl / t / 1e12 / peak_tf}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -445,6 +503,11 @@ def run_ours(args):
                    "seconds_per_maskgit_step": mean, "weights_init_s": ref.init_s,
                    "reference_decode_ops_s": {f"B{b}": reference_decode_ops_cpu(b, threads=threads) for b in (1, 16)}}
             del ref
+        iso_dec = iso_att = None
+        if world == 1 and not args.no_isolated:
+            from ml_unigen_b200 import ops as _ops
+            iso_dec = isolated_decode_points(torch, dev, _ops, peaks["hbm"])
+            iso_att = isolated_attention_point(torch, dev, _ops, peaks["tf_sust"])
         tr_mlp, src_mlp = _traffic("gemm_swiglu")
         tr_att, src_att = _traffic("omni_attention")
         tr_dec, src_dec = _traffic("decode_fast")
@@ -476,7 +539,10 @@ def run_ours(args):
                          "note": "launches of MaskGIT steps 1..17 (query rows = the N+2 image-block rows, keys = all rows; "
                                  "text-prefix K/V reuse); the 28 step-0 launches over all L rows are timed separately",
                          "step0_full_avg_launch_ms": (sum(attn_full_ms) / len(attn_full_ms)) if attn_full_ms else None,
-                         "step0_full_flops_per_launch": flops_full},
+                         "step0_full_flops_per_launch": flops_full,
+                         "isolated_window_pass": iso_att,
+                         "isolated_note": "the same launch alone (28 back to back, P = 0): no GEMMs holding the part at its power cap, SM clock "
+                                          "near 1.9 GHz instead of ~1.4 GHz; BASELINE.json configs[3]"},
             "roofline_decode": {"kernel": "decode_fast_kernel + select_kernel (one decode step)", "bound": "hbm",
                                 "achieved": live_bytes / dec_total / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                                 "frac": live_bytes / dec_total / 1e9 / peaks["hbm"], "traffic": tr_dec, "traffic_note": src_dec,
@@ -485,6 +551,9 @@ def run_ours(args):
                                 "step0_ms": dec0_avg * 1e3,
                                 "algorithmic_GBs_crediting_skipped_rows": (e - s) * N * V * 2 / dec_avg / 1e9,
                                 "reference_ops_same_gpu_ms": reference_decode_ops_gpu(torch, dev, e - s),
+                                "isolated_flat_step0": iso_dec,
+                                "isolated_note": "BASELINE.json configs[2]: the decode step alone, synthetic flat logits, all rows masked; the fixed "
+                                                 "~22 us of a launch pair weigh less as B grows (DESIGN.md 4.1)",
                                 "note": "`achieved` = bytes actually streamed (rows of still-masked tokens x V x 2 B, summed over the 18 mask states "
                                         "of the schedule) / time of all decode steps; step0_* = the all-rows state alone; reference_ops = the reference's "
                                         "torch op sequence (models/unigen.py:418-445) on this GPU at the same batch, flat logits"},
@@ -521,6 +590,7 @@ def main():
     ap.add_argument("--no-pixels", action="store_true", help="skip the MAGViT-v2 pixel-decoder timing after the measured path")
     ap.add_argument("--no-best-of-n", action="store_true", help="skip the Best-of-N (configs[4]) measurement after the measured path")
     ap.add_argument("--no-config2-sample", action="store_true", help="reference arm: skip the 1-step sample at the GPU arm's shape")
+    ap.add_argument("--no-isolated", action="store_true", help="skip the isolated decode-step / attention points (configs[2] / configs[3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
