@@ -185,6 +185,7 @@ struct AttnParams {
     int n_split;            // the last n_split pairs of the linear grid are cut into two one-tile CTAs, see the kernel
     int tail_rows;          // > 0: the last pair holds only this many query rows (Lq % 256) and is GQA-packed, see the kernel
     float* dbg;             // optional: dumps S and P of (b=0, h=0, q tile 0, kv tile 0)
+    int st256;              // the output rows are 32-byte aligned: the epilogue may use 32-byte stores
 };
 
 // Descriptor words.  The high word of every shared-memory descriptor used here is the same constant
@@ -861,11 +862,23 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             tc_fence_after();
             const float inv_l = 1.0f / l_run;
             __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.a.out) + (int64_t)b * p.a.o_sb + (int64_t)lrow * p.a.o_sl + (int64_t)ho * p.a.o_sh;
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(o_addr + ch * 32, v);
-                if (lrow < Lq && row_stored) {
+            // O row -> registers 32 columns at a time, two loads in flight (ping-pong); O_x is handed back to the MMA warp as soon as
+            // the last chunk is in registers, before its stores
+            auto store_chunk = [&](const uint32_t (&v)[32], int ch) {
+                if (lrow < Lq && row_stored && p.st256) {
+                    // 32-byte stores (STG.256): a lane writes whole 32-byte sectors of its own row.  The rows of a warp are 3 KB apart, so a
+                    // store instruction touches 32 sectors whatever its width: half as many instructions = half as many sector accesses
+                    // (the 16-byte version spent ~4 k cycles per item here, the epilogue's whole time)
+#pragma unroll
+                    for (int q = 0; q < 32; q += 16) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) w[e] = pack_bf16(__uint_as_float(v[q + 2 * e]) * inv_l, __uint_as_float(v[q + 2 * e + 1]) * inv_l);
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + ch * 32 + q), "r"(w[0]), "r"(w[1]),
+                                     "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                                     : "memory");
+                    }
+                } else if (lrow < Lq && row_stored) {
 #pragma unroll
                     for (int q = 0; q < 32; q += 8) {
                         uint4 o;
@@ -876,9 +889,24 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                         *reinterpret_cast<uint4*>(orow + ch * 32 + q) = o;
                     }
                 }
+            };
+            {
+                uint32_t ve[32], vf[32];
+                tmem_ld32_async(o_addr, ve);
+                tmem_ld32_async(o_addr + 32, vf);
+                tmem_ld_wait();
+                pin32(ve); pin32(vf);
+                store_chunk(ve, 0);
+                tmem_ld32_async(o_addr + 64, ve);
+                store_chunk(vf, 1);
+                tmem_ld32_async(o_addr + 96, vf);
+                tmem_ld_wait();
+                pin32(ve); pin32(vf);
+                tc_fence_before();
+                bar_arrive(&bars->o_free[x]);            // O_x has been read out: the next item may accumulate into it
+                store_chunk(ve, 2);
+                store_chunk(vf, 3);
             }
-            tc_fence_before();
-            bar_arrive(&bars->o_free[x]);                // O_x has been read out: the next item may accumulate into it
             if (r == 0) UG_TLI(2 + x, 3);
         }
     }
@@ -960,6 +988,7 @@ int launch_omni_attention(const AttnArgs& a, int num_sms, cudaStream_t stream, c
         p.n_split = k;
     }
     p.dbg = a.dbg;
+    p.st256 = (reinterpret_cast<uintptr_t>(a.out) % 32 == 0 && a.o_sb % 16 == 0 && a.o_sl % 16 == 0 && a.o_sh % 16 == 0) ? 1 : 0;
     static bool attr_set[64] = {};                       // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);

@@ -1,2 +1,3 @@
-ncu --set full --clock-control none --import-source on -f -k regex:gemm_tc_kernel --launch-skip 2 -c 1 -o gpurun_out/ncu_gemm_swiglu_r2 python tools/prof_gemm.py gate_up > gpurun_out/ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -f -k regex:gemm_tc_kernel --launch-skip 2 -c 1 -o gpurun_out/ncu_gemm_downres_r2 python tools/prof_gemm.py down_res > gpurun_out/ncu2.log 2>&1
+timeout 600 python -m pytest tests/test_omni_attention_gpu.py -x -q -m gpu 2>&1 | tail -3 > gpurun_out/exp_pytest.log
+QUICK=1 NO_SDPA=1 timeout 300 python tools/bench_attention.py > gpurun_out/exp_bench.log 2>&1
+timeout 120 python tools/attn_timeline.py > gpurun_out/tl_x.txt 2>&1
