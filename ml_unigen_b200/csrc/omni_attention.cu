@@ -328,11 +328,7 @@ __device__ __forceinline__ float prob_chunk(const uint32_t (&v)[32], uint32_t (&
     for (int q = 0; q < 32; q += 2) {
         const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[q]), __uint_as_float(v[q + 1])), c2, nm2);
         float2 e;
-#ifdef UG_ATTN_POLY8
-        if (((q >> 1) & 7) < UG_ATTN_POLY8) e = ex2_poly2(x);             // experiment: share in eighths
-#else
         if (((q >> 1) & 3) < UG_ATTN_POLY) e = ex2_poly2(x);              // compile-time choice per pair
-#endif
         else e = make_float2(ex2(x.x), ex2(x.y));
         if (kMasked) {
             const int col = cbase + q;
