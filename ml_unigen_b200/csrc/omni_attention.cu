@@ -269,6 +269,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 #define UG_ATTN_EARLYPUB 1   // 1: hand a P half to the MMA warp right after its stores (waits for them); 0: behind the next half's first load
                              //    (round 2, after the counters left local memory: 1 is 1-2 % faster; it was a wash before)
 #endif
+#ifndef UG_ATTN_TIMELINE
+#define UG_ATTN_TIMELINE 0   // 1: cycle stamps of CTA 0 into the debug buffer (tools/attn_timeline.py builds this variant)
+#endif
 #ifndef UG_ATTN_POLY
 #define UG_ATTN_POLY 1       // of every 4 pairs of exponentials, how many go to the FMA pipe (polynomial); 0 = all on MUFU
                              //    (round 2: 1 = a quarter of the exponentials: window pass 0.173 -> 0.164 ms; 2 is slower again: FMA issue)
@@ -450,13 +453,19 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    // test hook: cycle stamps of the first item of CTA 0 at dbg[32768 + role*512 + iter*8 + event]
+    // instrumentation (compiled in with -DUG_ATTN_TIMELINE=1 only, tools/attn_timeline.py): cycle stamps of the first item of CTA 0 at
+    // dbg[32768 + role*512 + iter*8 + event].  In the product build the macros are empty: their run-time conditions alone were
+    // 7 % of the kernel's executed instructions, most of them in the softmax warps' inner loop.
+#if UG_ATTN_TIMELINE
     bool tl = false;
     const uint32_t clk0 = (uint32_t)clock();
 #define UG_TL(role, iter, ev)                                                                            \
     do {                                                                                                 \
         if (tl && (iter) < 64) p.dbg[32768 + (role) * 512 + (iter) * 8 + (ev)] = (float)((uint32_t)clock() - clk0); \
     } while (0)
+#else
+#define UG_TL(role, iter, ev) do { } while (0)
+#endif
 
     // running state of the roles across items (every thread walks the same item sequence)
     int n_items = 0;                                  // items started by this CTA: phase of q_full / q_empty
@@ -559,13 +568,17 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int tA0 = it.tA0, tA1 = it.tA1, tB0 = it.tB0, tB1 = it.tB1, tU0 = it.tU0, tU1 = it.tU1, kv_off = it.kv_off;
     const unsigned long long hmask0 = it.hmask[0], hmask1 = it.hmask[1];
     auto half_on = [&](int x, int t, int hf) -> bool { return ((x ? hmask1 : hmask0) >> (2 * (t - tU0) + hf)) & 1ull; };
+#if UG_ATTN_TIMELINE
     tl = p.dbg && blockIdx.x == 0 && n_items == 0;
-    // item-boundary stamps of CTA 0 (test hook): dbg[32768 + 1536 + role * 128 + item * 8 + event], 16 items, 4 roles
+    // item-boundary stamps of CTA 0: dbg[32768 + 1536 + role * 128 + item * 8 + event], 16 items, 4 roles
     const bool tli = p.dbg && blockIdx.x == 0 && n_items < 16;
 #define UG_TLI(role, ev)                                                                                             \
     do {                                                                                                             \
         if (tli) p.dbg[32768 + 1536 + (role) * 128 + n_items * 8 + (ev)] = (float)((uint32_t)clock() - clk0);        \
     } while (0)
+#else
+#define UG_TLI(role, ev) do { } while (0)
+#endif
 
     if (warp == 8) {
         // =========================================================== TMA producer

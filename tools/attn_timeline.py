@@ -1,4 +1,6 @@
-"""Cycle-stamp timeline of one omni-attention CTA (debug hook): where a kv-tile iteration spends its time."""
+"""Cycle-stamp timeline of one omni-attention CTA: where a kv-tile iteration spends its time.
+Needs a library built with -DUG_ATTN_TIMELINE=1 (`bash tools/build_attn_variants.sh "-DUG_ATTN_TIMELINE=1"`, then
+`UNIGEN_B200_LIB=build/exp/lib__DUG_ATTN_TIMELINE_1.so python tools/attn_timeline.py`): the stamps are compiled out of the product."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
