@@ -269,6 +269,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 #define UG_ATTN_EARLYPUB 1   // 1: hand a P half to the MMA warp right after its stores (waits for them); 0: behind the next half's first load
                              //    (round 2, after the counters left local memory: 1 is 1-2 % faster; it was a wash before)
 #endif
+#ifndef UG_ATTN_DUMP
+#define UG_ATTN_DUMP 0       // 1: the score / probability tile dump behind `dbg` (failure diagnosis in tests/test_omni_attention_gpu.py)
+#endif
 #ifndef UG_ATTN_TIMELINE
 #define UG_ATTN_TIMELINE 0   // 1: cycle stamps of CTA 0 into the debug buffer (tools/attn_timeline.py builds this variant)
 #endif
@@ -749,7 +752,8 @@ omni_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             const float c = p.scale_log2;
             float m_ref = -INFINITY;                     // the (possibly stale) max the exponentials are taken against
             float l_run = 0.0f;
-            const bool dump = p.dbg && x == 0 && qp == 0 && h == 0 && b == 0;
+            // debug dump of S and P of (b = 0, h = 0, q tile 0, first kv tile): compiled in with -DUG_ATTN_DUMP=1 only
+            const bool dump = UG_ATTN_DUMP && p.dbg && x == 0 && qp == 0 && h == 0 && b == 0;
             bool o_live = false;                          // O_x holds (or is about to hold) an accumulation of THIS item
 
             // Optimistic online softmax: the exponentials of a 64-column half are taken against the current reference m_ref

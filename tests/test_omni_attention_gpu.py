@@ -44,7 +44,8 @@ def _check(out, ref, valid_rows=None, tag=""):
 
 
 def _diagnose(q, k, dump, P, S, scale):
-    """Localise a failure: compare the raw score tile S and the probability tile P of the debug dump."""
+    """Localise a failure: compare the raw score tile S and the probability tile P of the debug dump (filled only by a library built
+    with -DUG_ATTN_DUMP=1, `bash tools/build_attn_variants.sh "-DUG_ATTN_DUMP=1"` + UNIGEN_B200_LIB; zeros in the product build)."""
     L = q.shape[1]
     i0, j0 = 0, 0                      # the dump is q tile 0 x its first kv tile (tile 0) of (b=0, h=0)
     rows = min(128, L - i0)
