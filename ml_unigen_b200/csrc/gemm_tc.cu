@@ -193,29 +193,35 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtens
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
+// kStream: the tile is not read back soon (gate|up activation, logits, convolution outputs: larger than L2) -> evict_first;
+// the q/k/v tile is consumed by the attention launch that follows and keeps the default policy
+template <bool kStream = true>
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3)
 {
 #if UG_GEMM_L2HINT
+    if (kStream)
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;" ::"l"(map), "r"(src), "r"(c0),
                  "r"(c1), "r"(c2), "r"(c3), "l"(l2_policy_evict_first())
                  : "memory");
-#else
+    else
+#endif
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                  "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
-#endif
 }
+template <bool kStream = true>
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1)
 {
 #if UG_GEMM_L2HINT
+    if (kStream)
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map), "r"(src), "r"(c0),
                  "r"(c1), "l"(l2_policy_evict_first())
                  : "memory");
-#else
+    else
+#endif
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                  "r"(c1)
                  : "memory");
-#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -654,8 +660,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     fence_async_smem();
                     epi_bar();
                     if (issuer && m0 < p.M) {
-                        tma_store_2d(&tm_o, s_u32(stg), col0, m0);
-                        tma_store_2d(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
+                        tma_store_2d<false>(&tm_o, s_u32(stg), col0, m0);
+                        tma_store_2d<false>(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
                         bulk_commit();
                     }
                 }

@@ -1,4 +1,2 @@
-: > gpurun_out/exp_bench.log
-for L in ml_unigen_b200/csrc/libunigen_b200.so build/exp/lib_*.so; do
-  echo $L >> gpurun_out/exp_bench.log; UNIGEN_B200_LIB=$L QUICK=1 NO_SDPA=1 timeout 300 python tools/bench_attention.py >> gpurun_out/exp_bench.log 2>&1
-done
+timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_backbone_gpu.py -x -q -m gpu 2>&1 | tail -3 > gpurun_out/exp_pytest.log
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-pixels --no-best-of-n --no-isolated > gpurun_out/exp_benchpy.json 2>/dev/null
