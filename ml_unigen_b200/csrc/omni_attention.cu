@@ -6,19 +6,22 @@
 // is never materialised: it is the closed form of two integers per sequence (pad_len P_b,
 // soi_idx S_b) and fully masked KV tiles are skipped.
 //
-// One CTA = 256 query rows (two 128-row tiles A and B) of one (batch, q-head); 320 threads:
+// Persistent grid: one CTA per SM walks a static list of work items; an item = 256 query rows (two 128-row tiles A and B) of one
+// (batch, q-head), a GQA-packed tail tile, or one tile of a split pair.  384 threads:
 //   warps 0-3  softmax / correction / epilogue of tile A: thread r owns query row r (TMEM lane r)
 //   warps 4-7  the same for tile B
-//   warp  8    TMA producer: Q_A, Q_B once, then K_t / V_t tiles (2-deep rings), SWIZZLE_128B boxes
-//   warp  9    MMA issuer (one elected lane): S_x = Q_x K_t^T and O_x += P_x V_t with tcgen05.mma
-//              (kind::f16, bf16 x bf16 -> fp32, M=128 N=128 K=16), accumulators in TMEM
-// TMEM columns: S_A [0,128), S_B [128,256), O_A [256,384), O_B [384,512).  P_x (bf16 pairs) overwrites the
-// first 64 columns of S_x and is the A operand of the second GEMM straight from tensor memory, so the
-// probabilities never touch shared memory.  The two tiles ping-pong: while warpgroup A is in its softmax
-// the tensor core runs the GEMMs of tile B and vice versa; the issue order per kv tile is
-// PV_A(t), QK_A(t+1), PV_B(t), QK_B(t+1).  Row maxima are rescaled lazily (only when the true max moved by
-// more than 2^8), which is exact because O, l and P always share the same reference max.
-// GQA: the 6 query heads of a KV head read the same K/V tiles (L2 hits); nothing is expanded.
+//   warp  8    TMA producer: Q_A, Q_B per item, then K_t / V_t tiles (2-deep rings), SWIZZLE_128B boxes
+//   warps 9,10 MMA issuers of tile A / tile B: one elected thread runs the whole chain of its tile --
+//              S_x[hf] = Q_x K_t[hf]^T and O_x += P_x[hf] V_t[hf] with tcgen05.mma (kind::f16, bf16 x bf16 -> fp32), accumulators in TMEM
+//   warp  11   idle (keeps the third warpgroup whole)
+// TMEM columns: S_A [0,128), S_B [128,256), O_A [256,384), O_B [384,512).  Every query tile is pipelined in two 64-key halves, each a
+// chain of its own (scores -> softmax -> P V -> next scores); P_x[hf] (bf16 pairs) overwrites the first 32 columns of S_x[hf] and is
+// the A operand of the second GEMM straight from tensor memory, so the probabilities never touch shared memory.  The exponentials
+// are taken against a running reference without a max pass (optimistic online softmax: a stale reference shows in the row sum and
+// only then O, l and the half are redone -- exact, because O, l and P always share one reference); a quarter of them runs on the
+// FMA pipe (polynomial), the rest on MUFU.EX2.
+// GQA: the 6 query heads of a KV head read the same K/V tiles (L2 hits); nothing is expanded.  DESIGN.md section 4.2 has the
+// measurements, the timeline and the variants that were measured slower.
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
