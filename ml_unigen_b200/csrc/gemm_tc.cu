@@ -193,8 +193,8 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtens
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
-// kStream: the tile is not read back soon (gate|up activation, logits, convolution outputs: larger than L2) -> evict_first;
-// the q/k/v tile is consumed by the attention launch that follows and keeps the default policy
+// kStream: the tile is not read back soon (gate|up activation, convolution outputs: larger than L2) -> evict_first; the q/k/v tile
+// and the logits are consumed by the launch that follows and keep the default policy (measured: no difference for either)
 template <bool kStream = true>
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3)
 {
@@ -774,9 +774,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                                 tma_store_4d(&tm_o, s_u32(stg) + 16384, col0 + 64, cx, cy, cb);
                                 bulk_commit();
                             }
-                        } else if (issuer && m0 < p.M) {
-                            tma_store_2d(&tm_o, s_u32(stg), col0, m0);
-                            tma_store_2d(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
+                        } else if (issuer && m0 < p.M) {         // codebook head: the decode step reads the logits at once (default policy)
+                            tma_store_2d<false>(&tm_o, s_u32(stg), col0, m0);
+                            tma_store_2d<false>(&tm_o, s_u32(stg) + 16384, col0 + 64, m0);
                             bulk_commit();
                         }
                     }
